@@ -1,0 +1,80 @@
+"""Build libcoddvec.so (hand-written sm_100a CUDA + C-ABI) in-tree with nvcc.
+
+The translation units compile in parallel; objects are cached under build/ by source mtime.
+`python -m codd_query_engine_b200.build [--force]`
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+ROOT = PKG.parent
+CSRC = PKG / "csrc"
+OUT = PKG / "libcoddvec.so"
+OBJ_DIR = ROOT / "build" / "obj"
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC",
+    "-Xptxas", "-v",
+    "-diag-suppress", "177",
+]
+UNITS = ["coddvec.cu", "k2_inst_qb1.cu", "k2_inst_qb2.cu", "k2_inst_qb4.cu", "k3_mma.cu"]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _deps_mtime() -> float:
+    files = list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.hpp")) + [ROOT / "include" / "coddvec.h", Path(__file__)]
+    return max(f.stat().st_mtime for f in files)
+
+
+def _compile(unit: str, force: bool) -> Path:
+    src = CSRC / unit
+    obj = OBJ_DIR / (src.stem + ".o")
+    log = OBJ_DIR / (src.stem + ".ptxas.log")
+    newest = max(src.stat().st_mtime, _deps_mtime())
+    if not force and obj.exists() and obj.stat().st_mtime >= newest:
+        return obj
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
+    cmd = [_nvcc(), *NVCC_FLAGS, "-ccbin", "/usr/bin/g++", "-c", str(src), "-o", str(obj)]
+    proc = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    log.write_text(proc.stderr)
+    if proc.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {unit}:\n{proc.stderr[-4000:]}")
+    return obj
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    OBJ_DIR.mkdir(parents=True, exist_ok=True)
+    units = [u for u in UNITS if (CSRC / u).exists()]
+    with ThreadPoolExecutor(max_workers=min(len(units), os.cpu_count() or 4)) as pool:
+        objs = list(pool.map(lambda u: _compile(u, force), units))
+    if force or not OUT.exists() or any(o.stat().st_mtime > OUT.stat().st_mtime for o in objs):
+        env = dict(os.environ)
+        env.pop("CC", None)
+        env.pop("CXX", None)
+        cmd = [_nvcc(), "-shared", "-cudart", "static", "-ccbin", "/usr/bin/g++",
+               "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(OUT), *map(str, objs)]
+        proc = subprocess.run(cmd, capture_output=True, text=True, env=env)
+        if proc.returncode != 0:
+            raise RuntimeError(f"link failed:\n{proc.stderr[-4000:]}")
+    if verbose:
+        print(f"built {OUT}")
+    return OUT
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose=True)

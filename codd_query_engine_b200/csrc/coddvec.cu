@@ -1,0 +1,719 @@
+// coddvec.cu -- host runtime + C-ABI of libcoddvec.so (see include/coddvec.h).
+//
+// Everything the reference delegates to the third-party chromadb client for the
+// `search_relevant_metrics` path (codd_dal/metrics/metrics_semantic_metadata_store.py:60-69,
+// :236-238, :260, :314-316) that is data-parallel lives here: the device-resident corpus, K1
+// normalise/append, K2 streaming scan, K3 tensor-core scoring, K4 merge.  No CPU fallback.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <shared_mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#define CV_MAIN_TU 1
+#include "../../include/coddvec.h"
+#include "common.cuh"
+#include "k1_normalise.cuh"
+#include "k2_scan.cuh"
+#include "k3_mma.cuh"
+#include "vmm.hpp"
+
+namespace {
+
+using namespace cv;
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CV_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            (void)cudaGetLastError();                                                              \
+            return fail(e__ == cudaErrorMemoryAllocation ? CV_ERR_OOM : CV_ERR_CUDA, "%s failed: %s (%s:%d)", \
+                        #call, cudaGetErrorString(e__), __FILE__, __LINE__);                       \
+        }                                                                                          \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { (void)cudaGetLastError(); prev = -1; }
+        ok = cudaSetDevice(dev) == cudaSuccess;
+        if (!ok) (void)cudaGetLastError();
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) (void)cudaSetDevice(prev);
+    }
+};
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;  // elements
+    int reserve(size_t n) {
+        if (n <= cap) return CV_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 2 + 64;
+        CV_CUDA(cudaMalloc(&p, want * sizeof(T)));
+        cap = want;
+        return CV_OK;
+    }
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+
+template <typename T>
+struct PinBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t n) {
+        if (n <= cap) return CV_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 2 + 64;
+        CV_CUDA(cudaMallocHost(&p, want * sizeof(T)));
+        cap = want;
+        return CV_OK;
+    }
+    ~PinBuf() { if (p) cudaFreeHost(p); }
+};
+
+// Per-query scratch.  A context is used by one query batch at a time; `busy` orders reuse on a
+// different stream without blocking the host.
+struct QueryCtx {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t busy = nullptr;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    bool timed = false;
+    DevBuf<float> d_q;
+    DevBuf<uint64_t> d_partial;
+    DevBuf<uint64_t> d_out;
+    DevBuf<uint32_t> d_mask;
+    cv::MmaScratch mma;  // K3 scratch (bf16 queries, per-CTA lists)
+    unsigned int* d_counter = nullptr;
+    PinBuf<float> h_q;
+    PinBuf<uint64_t> h_out;
+    struct Plan { cv::ScanFn fn; int grid; size_t smem; };
+    std::unordered_map<int, Plan> plans;  // (qb, pred, k) -> launch plan
+    ~QueryCtx() {
+        if (d_counter) cudaFree(d_counter);
+        if (mma.p) cudaFree(mma.p);
+        if (busy) cudaEventDestroy(busy);
+        if (t0) cudaEventDestroy(t0);
+        if (t1) cudaEventDestroy(t1);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+}  // namespace
+
+struct cv_index {
+    cv_config cfg{};
+    int D = 0, Dp = 0, C = 0;
+    int sm_count = 148;
+    int64_t max_rows = 0;
+    VmmArray E, scale, ns, label;
+    std::atomic<int64_t> n_committed{0};
+    int64_t capacity_rows = 0;
+
+    std::mutex upsert_mu;          // serialises writers
+    std::shared_mutex overwrite_mu;  // writers overwriting live rows exclude query enqueue
+    cudaStream_t upsert_stream = nullptr;
+    DevBuf<float> stage_x;
+    DevBuf<uint32_t> stage_ns, stage_label;
+    DevBuf<int64_t> stage_rows;
+    unsigned int* d_flag = nullptr;
+
+    std::mutex ctx_mu;
+    std::vector<std::unique_ptr<QueryCtx>> ctx_all;  // owner
+    std::vector<QueryCtx*> ctx_free;                  // idle contexts
+
+    std::atomic<int64_t> queries{0}, launches{0}, upserted{0};
+    std::mutex stats_mu;
+    QueryCtx* last_timed = nullptr;
+    int64_t last_bytes = 0;
+    int32_t last_path = 0;
+    std::atomic<int32_t> profiling{0};
+
+    ~cv_index() {
+        ctx_free.clear();
+        ctx_all.clear();
+        if (d_flag) cudaFree(d_flag);
+        if (upsert_stream) cudaStreamDestroy(upsert_stream);
+    }
+};
+
+namespace {
+
+int ensure_capacity(cv_index* idx, int64_t rows) {
+    if (rows <= idx->capacity_rows) return CV_OK;
+    if (rows > idx->max_rows)
+        return fail(CV_ERR_INVALID, "index is full: %lld rows requested, max_rows = %lld", (long long)rows,
+                    (long long)idx->max_rows);
+    auto grow = [&](VmmArray& a, size_t bytes) -> int {
+        std::string e = a.ensure(bytes);
+        if (e.empty()) return CV_OK;
+        return fail(e.rfind("OOM", 0) == 0 ? CV_ERR_OOM : CV_ERR_CUDA, "%s", e.c_str());
+    };
+    int rc;
+    if ((rc = grow(idx->E, static_cast<size_t>(rows) * idx->Dp * 2))) return rc;
+    if ((rc = grow(idx->scale, static_cast<size_t>(rows) * 4))) return rc;
+    if ((rc = grow(idx->ns, static_cast<size_t>(rows) * 4))) return rc;
+    if ((rc = grow(idx->label, static_cast<size_t>(rows) * 4))) return rc;
+    int64_t cap = static_cast<int64_t>(idx->E.mapped_bytes() / (static_cast<size_t>(idx->Dp) * 2));
+    cap = std::min<int64_t>(cap, idx->scale.mapped_bytes() / 4);
+    cap = std::min<int64_t>(cap, idx->ns.mapped_bytes() / 4);
+    cap = std::min<int64_t>(cap, idx->label.mapped_bytes() / 4);
+    idx->capacity_rows = std::min(cap, idx->max_rows);
+    return CV_OK;
+}
+
+int acquire_ctx(cv_index* idx, QueryCtx** out) {
+    {
+        std::lock_guard<std::mutex> g(idx->ctx_mu);
+        if (!idx->ctx_free.empty()) {
+            *out = idx->ctx_free.back();
+            idx->ctx_free.pop_back();
+            return CV_OK;
+        }
+    }
+    std::unique_ptr<QueryCtx> c(new QueryCtx());
+    CV_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CV_CUDA(cudaEventCreateWithFlags(&c->busy, cudaEventDisableTiming));
+    CV_CUDA(cudaEventCreate(&c->t0));
+    CV_CUDA(cudaEventCreate(&c->t1));
+    CV_CUDA(cudaMalloc(&c->d_counter, 64 * sizeof(unsigned int)));
+    CV_CUDA(cudaMemset(c->d_counter, 0, 64 * sizeof(unsigned int)));
+    CV_CUDA(cudaEventRecord(c->busy, c->stream));
+    {
+        std::lock_guard<std::mutex> g(idx->ctx_mu);
+        *out = c.get();
+        idx->ctx_all.push_back(std::move(c));
+    }
+    return CV_OK;
+}
+
+void release_ctx(cv_index* idx, QueryCtx* c) {
+    std::lock_guard<std::mutex> g(idx->ctx_mu);
+    idx->ctx_free.push_back(c);
+}
+
+// ------------------------------------------------------------------------------------------ K2 dispatch
+// (instantiations live in k2_inst_qb{1,2,4}.cu so that they compile in parallel)
+ScanFn pick_scan(int nch, int qb, bool pred) {
+    switch (qb) {
+        case 1: return pick_scan_qb1(nch, pred);
+        case 2: return pick_scan_qb2(nch, pred);
+        case 4: return pick_scan_qb4(nch, pred);
+        default: return nullptr;
+    }
+}
+
+struct ScanLaunch {
+    ScanFn fn;
+    int grid;
+    size_t smem;
+};
+
+int plan_scan(cv_index* idx, QueryCtx* c, int qb, int k, bool pred, ScanLaunch* out) {
+    const int plan_key = qb | (pred ? 16 : 0) | (k << 8);
+    auto it = c->plans.find(plan_key);
+    if (it != c->plans.end()) {
+        out->fn = it->second.fn;
+        out->grid = it->second.grid;
+        out->smem = it->second.smem;
+        return CV_OK;
+    }
+    const int nch = (idx->C + 15) / 16;
+    ScanFn fn = pick_scan(nch, qb, pred);
+    if (!fn) return fail(CV_ERR_UNSUPPORTED, "scan path: no kernel for dim=%d with %d queries per pass", idx->D, qb);
+    size_t smem = (static_cast<size_t>(kSelCap) + static_cast<size_t>(kScanWarps) * qb * k) * sizeof(uint64_t);
+    CV_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    int occ = 0;
+    CV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kScanThreads, smem));
+    if (occ < 1) return fail(CV_ERR_CUDA, "scan kernel cannot be resident (smem=%zu)", smem);
+    if (occ > 8) occ = 8;
+    out->fn = fn;
+    out->grid = idx->sm_count * occ;
+    out->smem = smem;
+    c->plans[plan_key] = QueryCtx::Plan{fn, out->grid, smem};
+    return CV_OK;
+}
+
+// Enqueue one query batch on `stream`.  d_q: [B][D] fp32 device, d_out: [B][k] device keys.
+int enqueue_query(cv_index* idx, QueryCtx* c, cudaStream_t stream, const float* d_q, const cv_query_params* p,
+                  const uint32_t* d_mask, uint64_t* d_out) {
+    const int B = p->n_queries, k = p->k;
+    const int64_t n = idx->n_committed.load(std::memory_order_acquire);
+    const bool pred = d_mask != nullptr || p->ns_code != CV_ANY || p->label_code != CV_ANY;
+    if (n == 0) {
+        CV_CUDA(cudaMemsetAsync(d_out, 0, sizeof(uint64_t) * B * k, stream));
+        return CV_OK;
+    }
+    const int nch = (idx->C + 15) / 16;
+    int path = p->path;
+    const int max_qb = scan_max_qb(nch);
+    if (path == CV_PATH_AUTO) path = (B <= max_qb || !mma_supported(idx->Dp)) ? CV_PATH_SCAN : CV_PATH_MMA;
+    const bool timed = idx->profiling.load() != 0;
+    if (timed) CV_CUDA(cudaEventRecord(c->t0, stream));
+    int64_t passes_bytes = 0;
+
+    if (path == CV_PATH_MMA) {
+        MmaArgs m;
+        m.E = idx->E.ptr<void>();
+        m.scale = idx->scale.ptr<float>();
+        m.ns = idx->ns.ptr<uint32_t>();
+        m.label = idx->label.ptr<uint32_t>();
+        m.mask = d_mask;
+        m.ns_code = p->ns_code;
+        m.label_code = p->label_code;
+        m.n = n;
+        m.D = idx->D;
+        m.Dp = idx->Dp;
+        m.cosine = idx->cfg.metric == CV_METRIC_COSINE;
+        m.row_offset = static_cast<uint32_t>(idx->cfg.row_offset);
+        m.q = d_q;
+        m.B = B;
+        m.k = k;
+        m.out = d_out;
+        m.counter = c->d_counter;
+        m.sm_count = idx->sm_count;
+        m.stream = stream;
+        int rc = mma_enqueue(m, c->mma, &idx->launches);
+        if (rc != 0) return fail(rc, "%s", mma_error().c_str());
+        passes_bytes = n * (2ll * idx->Dp + 4) * ((B + 255) / 256);
+    } else {
+        if (max_qb == 0)
+            return fail(CV_ERR_UNSUPPORTED, "scan path supports dim <= 1024 (got %d)", idx->D);
+        int done = 0;
+        while (done < B) {
+            int qb = 1;
+            while (qb * 2 <= max_qb && qb * 2 <= B - done) qb *= 2;
+            ScanLaunch L;
+            int rc = plan_scan(idx, c, qb, k, pred, &L);
+            if (rc) return rc;
+            rc = c->d_partial.reserve(static_cast<size_t>(qb) * L.grid * k);
+            if (rc) return rc;
+            ScanArgs a;
+            a.E = idx->E.ptr<uint4>();
+            a.scale = idx->scale.ptr<float>();
+            a.ns = idx->ns.ptr<uint32_t>();
+            a.label = idx->label.ptr<uint32_t>();
+            a.mask = d_mask;
+            a.ns_code = p->ns_code;
+            a.label_code = p->label_code;
+            a.n = n;
+            a.C = idx->C;
+            a.D = idx->D;
+            a.cosine = idx->cfg.metric == CV_METRIC_COSINE;
+            a.q = d_q + static_cast<size_t>(done) * idx->D;
+            a.k = k;
+            a.row_offset = static_cast<uint32_t>(idx->cfg.row_offset);
+            a.partial = c->d_partial.p;
+            a.counter = c->d_counter;
+            a.out = d_out + static_cast<size_t>(done) * k;
+            L.fn<<<L.grid, kScanThreads, L.smem, stream>>>(a);
+            CV_CUDA(cudaGetLastError());
+            idx->launches.fetch_add(1);
+            passes_bytes += n * (2ll * idx->Dp + 4);
+            done += qb;
+        }
+    }
+    if (timed) {
+        CV_CUDA(cudaEventRecord(c->t1, stream));
+        c->timed = true;
+        std::lock_guard<std::mutex> g(idx->stats_mu);
+        idx->last_timed = c;
+        idx->last_bytes = passes_bytes;
+    }
+    {
+        std::lock_guard<std::mutex> g(idx->stats_mu);
+        idx->last_path = path;
+    }
+    idx->queries.fetch_add(1);
+    return CV_OK;
+}
+
+int check_query_params(const cv_index* idx, const void* q, const cv_query_params* p) {
+    if (!idx || !q || !p) return fail(CV_ERR_INVALID, "null argument");
+    if (p->n_queries < 1) return fail(CV_ERR_INVALID, "n_queries must be >= 1 (got %d)", p->n_queries);
+    if (p->k < 1 || p->k > CV_MAX_K) return fail(CV_ERR_INVALID, "k must be in [1, %d] (got %d)", CV_MAX_K, p->k);
+    if (p->path != CV_PATH_AUTO && p->path != CV_PATH_SCAN && p->path != CV_PATH_MMA)
+        return fail(CV_ERR_INVALID, "unknown path %d", p->path);
+    return CV_OK;
+}
+
+}  // namespace
+
+// =============================================================================================== C-ABI
+extern "C" {
+
+const char* cv_last_error(void) { return g_err.c_str(); }
+const char* cv_version(void) { return "coddvec 0.1.0 (sm_100a)"; }
+
+uint64_t cv_encode_key(float score, uint32_t global_row) { return cv::pack_key(score, global_row); }
+
+void cv_decode_keys(const uint64_t* keys, int64_t n, float* out_scores, int64_t* out_rows) {
+    for (int64_t i = 0; i < n; ++i) {
+        const uint64_t key = keys[i];
+        if (key == 0) {
+            if (out_scores) out_scores[i] = 0.0f;
+            if (out_rows) out_rows[i] = -1;
+        } else {
+            if (out_scores) out_scores[i] = cv::key_score(key);
+            if (out_rows) out_rows[i] = static_cast<int64_t>(cv::key_row(key));
+        }
+    }
+}
+
+int cv_create(const cv_config* cfg, cv_index** out) {
+    if (!cfg || !out) return fail(CV_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->dim < 1 || cfg->dim > CV_MAX_DIM) return fail(CV_ERR_INVALID, "dim must be in [1, %d] (got %d)", CV_MAX_DIM, cfg->dim);
+    if (cfg->metric != CV_METRIC_COSINE && cfg->metric != CV_METRIC_IP)
+        return fail(CV_ERR_UNSUPPORTED, "unsupported metric %d (cosine and ip only)", cfg->metric);
+    if (cfg->capacity_rows < 0 || cfg->max_rows < 0 || cfg->row_offset < 0)
+        return fail(CV_ERR_INVALID, "negative capacity / max_rows / row_offset");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        (void)cudaGetLastError();
+        return fail(CV_ERR_CUDA, "no CUDA device available (%s); coddvec has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(CV_ERR_INVALID, "device %d out of range [0, %d)", cfg->device, ndev);
+    DeviceGuard dg(cfg->device);
+    if (!dg.ok) return fail(CV_ERR_CUDA, "cudaSetDevice(%d) failed", cfg->device);
+    CV_CUDA(cudaFree(nullptr));  // create the primary context
+    cudaDeviceProp prop;
+    CV_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10)
+        return fail(CV_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                    cfg->device, prop.major, prop.minor);
+
+    std::unique_ptr<cv_index> idx(new cv_index());
+    idx->cfg = *cfg;
+    idx->D = cfg->dim;
+    idx->Dp = (cfg->dim + 63) / 64 * 64;
+    idx->C = idx->Dp / 8;
+    idx->sm_count = prop.multiProcessorCount;
+    idx->max_rows = cfg->max_rows > 0 ? cfg->max_rows : (int64_t(1) << 28);
+    if (cfg->capacity_rows > idx->max_rows) idx->max_rows = cfg->capacity_rows;
+    if (cfg->row_offset + idx->max_rows > (int64_t(1) << 32) - 1)
+        return fail(CV_ERR_INVALID, "row_offset + max_rows exceeds the 32-bit global row space");
+
+    std::string err;
+    if (!(err = idx->E.reserve(cfg->device, static_cast<size_t>(idx->max_rows) * idx->Dp * 2)).empty() ||
+        !(err = idx->scale.reserve(cfg->device, static_cast<size_t>(idx->max_rows) * 4)).empty() ||
+        !(err = idx->ns.reserve(cfg->device, static_cast<size_t>(idx->max_rows) * 4)).empty() ||
+        !(err = idx->label.reserve(cfg->device, static_cast<size_t>(idx->max_rows) * 4)).empty())
+        return fail(CV_ERR_CUDA, "%s", err.c_str());
+    CV_CUDA(cudaStreamCreateWithFlags(&idx->upsert_stream, cudaStreamNonBlocking));
+    CV_CUDA(cudaMalloc(&idx->d_flag, sizeof(unsigned int)));
+    if (cfg->capacity_rows > 0) {
+        int rc = ensure_capacity(idx.get(), cfg->capacity_rows);
+        if (rc) return rc;
+    }
+    *out = idx.release();
+    return CV_OK;
+}
+
+void cv_destroy(cv_index* idx) {
+    if (!idx) return;
+    DeviceGuard dg(idx->cfg.device);
+    (void)cudaDeviceSynchronize();
+    delete idx;
+}
+
+int64_t cv_count(const cv_index* idx) { return idx ? idx->n_committed.load(std::memory_order_acquire) : 0; }
+int32_t cv_dim(const cv_index* idx) { return idx ? idx->D : 0; }
+
+int cv_set_profiling(cv_index* idx, int32_t enabled) {
+    if (!idx) return fail(CV_ERR_INVALID, "null index");
+    idx->profiling.store(enabled ? 1 : 0);
+    return CV_OK;
+}
+
+int cv_synchronize(cv_index* idx) {
+    if (!idx) return fail(CV_ERR_INVALID, "null index");
+    DeviceGuard dg(idx->cfg.device);
+    CV_CUDA(cudaDeviceSynchronize());
+    return CV_OK;
+}
+
+static int upsert_impl(cv_index* idx, const int64_t* rows, const float* emb, const uint32_t* ns_codes,
+                       const uint32_t* label_codes, int64_t n, int64_t* out_rows, bool on_device) {
+    if (!idx) return fail(CV_ERR_INVALID, "null index");
+    if (n < 0) return fail(CV_ERR_INVALID, "negative row count");
+    if (n == 0) return CV_OK;
+    if (!emb) return fail(CV_ERR_INVALID, "null embeddings");
+    DeviceGuard dg(idx->cfg.device);
+    if (!dg.ok) return fail(CV_ERR_CUDA, "cudaSetDevice(%d) failed", idx->cfg.device);
+    std::lock_guard<std::mutex> wg(idx->upsert_mu);
+
+    const int64_t committed = idx->n_committed.load(std::memory_order_acquire);
+    // resolve destination rows: appends get committed, committed+1, ...
+    std::vector<int64_t> dst(static_cast<size_t>(n));
+    int64_t appended = 0;
+    bool overwrite = false;
+    for (int64_t i = 0; i < n; ++i) {
+        int64_t r = rows ? rows[i] : -1;
+        if (r < 0) {
+            dst[i] = committed + appended++;
+        } else {
+            if (r >= committed) return fail(CV_ERR_INVALID, "row %lld is not committed (count = %lld)", (long long)r, (long long)committed);
+            dst[i] = r;
+            overwrite = true;
+        }
+    }
+    if (overwrite && !on_device) {
+        // overwrites destroy live rows: reject non-finite input before touching anything
+        for (int64_t i = 0; i < n; ++i) {
+            if (rows[i] < 0) continue;
+            const float* r = emb + i * idx->D;
+            for (int d = 0; d < idx->D; ++d) {
+                uint32_t u;
+                memcpy(&u, r + d, 4);
+                if ((u & 0x7F800000u) == 0x7F800000u)
+                    return fail(CV_ERR_NONFINITE, "embedding %lld contains NaN/Inf", (long long)i);
+            }
+        }
+    }
+    int rc = ensure_capacity(idx, committed + appended);
+    if (rc) return rc;
+
+    std::unique_lock<std::shared_mutex> ow(idx->overwrite_mu, std::defer_lock);
+    cudaStream_t s = idx->upsert_stream;
+    if (overwrite) {
+        ow.lock();  // no query may be enqueued while live rows are being rewritten
+        std::lock_guard<std::mutex> g(idx->ctx_mu);
+        for (auto& c : idx->ctx_all) CV_CUDA(cudaStreamWaitEvent(s, c->busy, 0));
+    }
+
+    const int64_t chunk_rows = std::max<int64_t>(1, std::min<int64_t>(n, (int64_t(64) << 20) / (4ll * idx->D)));
+    if (!on_device) {
+        if ((rc = idx->stage_x.reserve(static_cast<size_t>(chunk_rows) * idx->D))) return rc;
+        if (ns_codes && (rc = idx->stage_ns.reserve(chunk_rows))) return rc;
+        if (label_codes && (rc = idx->stage_label.reserve(chunk_rows))) return rc;
+    }
+    if ((rc = idx->stage_rows.reserve(chunk_rows))) return rc;
+    CV_CUDA(cudaMemsetAsync(idx->d_flag, 0, sizeof(unsigned int), s));
+
+    for (int64_t lo = 0; lo < n; lo += chunk_rows) {
+        const int64_t m = std::min(chunk_rows, n - lo);
+        NormArgs a;
+        if (on_device) {
+            a.x = emb + lo * idx->D;
+            a.ns_in = ns_codes ? ns_codes + lo : nullptr;
+            a.label_in = label_codes ? label_codes + lo : nullptr;
+        } else {
+            CV_CUDA(cudaMemcpyAsync(idx->stage_x.p, emb + lo * idx->D, sizeof(float) * m * idx->D, cudaMemcpyHostToDevice, s));
+            if (ns_codes) CV_CUDA(cudaMemcpyAsync(idx->stage_ns.p, ns_codes + lo, sizeof(uint32_t) * m, cudaMemcpyHostToDevice, s));
+            if (label_codes) CV_CUDA(cudaMemcpyAsync(idx->stage_label.p, label_codes + lo, sizeof(uint32_t) * m, cudaMemcpyHostToDevice, s));
+            a.x = idx->stage_x.p;
+            a.ns_in = ns_codes ? idx->stage_ns.p : nullptr;
+            a.label_in = label_codes ? idx->stage_label.p : nullptr;
+        }
+        CV_CUDA(cudaMemcpyAsync(idx->stage_rows.p, dst.data() + lo, sizeof(int64_t) * m, cudaMemcpyHostToDevice, s));
+        a.dst_rows = idx->stage_rows.p;
+        a.base_row = 0;
+        a.n = m;
+        a.D = idx->D;
+        a.Dp = idx->Dp;
+        a.cosine = idx->cfg.metric == CV_METRIC_COSINE;
+        a.E = idx->E.ptr<__nv_bfloat16>();
+        a.scale = idx->scale.ptr<float>();
+        a.ns = idx->ns.ptr<uint32_t>();
+        a.label = idx->label.ptr<uint32_t>();
+        const int64_t total = m * idx->D;
+        int cgrid = static_cast<int>(std::min<int64_t>((total + 255) / 256, idx->sm_count * 8));
+        k_count_nonfinite<<<cgrid, 256, 0, s>>>(a.x, total, idx->d_flag);
+        CV_CUDA(cudaGetLastError());
+        if (overwrite && on_device) {
+            // cannot pre-check on the host: stop before K1 if this chunk is bad
+            unsigned int bad = 0;
+            CV_CUDA(cudaMemcpyAsync(&bad, idx->d_flag, sizeof(bad), cudaMemcpyDeviceToHost, s));
+            CV_CUDA(cudaStreamSynchronize(s));
+            if (bad) return fail(CV_ERR_NONFINITE, "embeddings contain %u NaN/Inf values", bad);
+        }
+        int grid = static_cast<int>(std::min<int64_t>((m + 7) / 8, idx->sm_count * 8));
+        k_normalise_append<<<grid, 256, 0, s>>>(a);
+        CV_CUDA(cudaGetLastError());
+        idx->launches.fetch_add(2);
+        if (!on_device || lo + chunk_rows < n) CV_CUDA(cudaStreamSynchronize(s));  // staging buffers are reused
+    }
+    unsigned int bad = 0;
+    CV_CUDA(cudaMemcpyAsync(&bad, idx->d_flag, sizeof(bad), cudaMemcpyDeviceToHost, s));
+    CV_CUDA(cudaStreamSynchronize(s));
+    if (bad) return fail(CV_ERR_NONFINITE, "embeddings contain %u NaN/Inf values; nothing was committed", bad);
+    idx->n_committed.store(committed + appended, std::memory_order_release);
+    idx->upserted.fetch_add(n);
+    if (out_rows) memcpy(out_rows, dst.data(), sizeof(int64_t) * n);
+    return CV_OK;
+}
+
+int cv_upsert(cv_index* idx, const int64_t* rows, const float* emb, const uint32_t* ns_codes,
+              const uint32_t* label_codes, int64_t n, int64_t* out_rows) {
+    return upsert_impl(idx, rows, emb, ns_codes, label_codes, n, out_rows, false);
+}
+
+int cv_upsert_device(cv_index* idx, const int64_t* rows, const float* d_emb, const uint32_t* d_ns_codes,
+                     const uint32_t* d_label_codes, int64_t n, int64_t* out_rows) {
+    return upsert_impl(idx, rows, d_emb, d_ns_codes, d_label_codes, n, out_rows, true);
+}
+
+int cv_query_device(cv_index* idx, const float* d_q, const cv_query_params* p, uint64_t* d_out_keys, void* stream) {
+    int rc = check_query_params(idx, d_q, p);
+    if (rc) return rc;
+    if (!d_out_keys) return fail(CV_ERR_INVALID, "null output");
+    DeviceGuard dg(idx->cfg.device);
+    if (!dg.ok) return fail(CV_ERR_CUDA, "cudaSetDevice(%d) failed", idx->cfg.device);
+    std::shared_lock<std::shared_mutex> rd(idx->overwrite_mu);
+    QueryCtx* c = nullptr;
+    if ((rc = acquire_ctx(idx, &c))) return rc;
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+    cudaError_t e = cudaStreamWaitEvent(s, c->busy, 0);
+    if (e == cudaSuccess) {
+        rc = enqueue_query(idx, c, s, d_q, p, p->mask, d_out_keys);
+        e = cudaEventRecord(c->busy, s);
+    }
+    release_ctx(idx, c);
+    if (e != cudaSuccess) return fail(CV_ERR_CUDA, "stream ordering failed: %s", cudaGetErrorString(e));
+    return rc;
+}
+
+int cv_query(cv_index* idx, const float* q, const cv_query_params* p, float* out_scores, int64_t* out_rows,
+             int32_t* out_counts) {
+    int rc = check_query_params(idx, q, p);
+    if (rc) return rc;
+    const int B = p->n_queries, k = p->k;
+    const size_t qn = static_cast<size_t>(B) * idx->D;
+    for (size_t i = 0; i < qn; ++i) {
+        uint32_t u;
+        memcpy(&u, q + i, 4);
+        if ((u & 0x7F800000u) == 0x7F800000u) return fail(CV_ERR_NONFINITE, "query %zu contains NaN/Inf", i / idx->D);
+    }
+    DeviceGuard dg(idx->cfg.device);
+    if (!dg.ok) return fail(CV_ERR_CUDA, "cudaSetDevice(%d) failed", idx->cfg.device);
+    std::shared_lock<std::shared_mutex> rd(idx->overwrite_mu);
+    QueryCtx* c = nullptr;
+    if ((rc = acquire_ctx(idx, &c))) return rc;
+    struct Releaser {
+        cv_index* i; QueryCtx* c;
+        ~Releaser() { release_ctx(i, c); }
+    } rel{idx, c};
+    cudaStream_t s = c->stream;
+    CV_CUDA(cudaStreamWaitEvent(s, c->busy, 0));
+    if ((rc = c->d_q.reserve(qn)) || (rc = c->h_q.reserve(qn)) || (rc = c->d_out.reserve(static_cast<size_t>(B) * k)) ||
+        (rc = c->h_out.reserve(static_cast<size_t>(B) * k)))
+        return rc;
+    memcpy(c->h_q.p, q, qn * sizeof(float));
+    CV_CUDA(cudaMemcpyAsync(c->d_q.p, c->h_q.p, qn * sizeof(float), cudaMemcpyHostToDevice, s));
+    const uint32_t* d_mask = nullptr;
+    if (p->mask) {
+        const int64_t n = idx->n_committed.load(std::memory_order_acquire);
+        const size_t words = static_cast<size_t>((n + 31) / 32);
+        if (words) {
+            if ((rc = c->d_mask.reserve(words))) return rc;
+            CV_CUDA(cudaMemcpyAsync(c->d_mask.p, p->mask, words * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+            d_mask = c->d_mask.p;
+        }
+    }
+    rc = enqueue_query(idx, c, s, c->d_q.p, p, d_mask, c->d_out.p);
+    if (rc) { (void)cudaStreamSynchronize(s); return rc; }
+    CV_CUDA(cudaMemcpyAsync(c->h_out.p, c->d_out.p, sizeof(uint64_t) * B * k, cudaMemcpyDeviceToHost, s));
+    CV_CUDA(cudaEventRecord(c->busy, s));
+    CV_CUDA(cudaStreamSynchronize(s));
+    cv_decode_keys(c->h_out.p, static_cast<int64_t>(B) * k, out_scores, out_rows);
+    if (out_counts) {
+        for (int b = 0; b < B; ++b) {
+            int cnt = 0;
+            while (cnt < k && c->h_out.p[static_cast<size_t>(b) * k + cnt] != 0) ++cnt;
+            out_counts[b] = cnt;
+        }
+    }
+    return CV_OK;
+}
+
+int cv_merge_keys_device(int32_t device, const uint64_t* d_keys_in, int32_t G, int32_t B, int32_t k_in, int32_t k_out,
+                         uint64_t* d_keys_out, void* stream) {
+    if (!d_keys_in || !d_keys_out) return fail(CV_ERR_INVALID, "null argument");
+    if (G < 1 || B < 1 || k_in < 1 || k_out < 1 || k_out > CV_MAX_K)
+        return fail(CV_ERR_INVALID, "bad merge shape G=%d B=%d k_in=%d k_out=%d", G, B, k_in, k_out);
+    DeviceGuard dg(device);
+    if (!dg.ok) return fail(CV_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    k_merge_keys<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_keys_in, G, B, k_in, k_out, d_keys_out);
+    CV_CUDA(cudaGetLastError());
+    return CV_OK;
+}
+
+int cv_get_rows(cv_index* idx, const int64_t* rows, int64_t n, uint16_t* out_bf16, float* out_scale, uint32_t* out_ns,
+                uint32_t* out_label) {
+    if (!idx || (!rows && n > 0)) return fail(CV_ERR_INVALID, "null argument");
+    DeviceGuard dg(idx->cfg.device);
+    if (!dg.ok) return fail(CV_ERR_CUDA, "cudaSetDevice(%d) failed", idx->cfg.device);
+    const int64_t committed = idx->n_committed.load(std::memory_order_acquire);
+    for (int64_t i = 0; i < n; ++i)
+        if (rows[i] < 0 || rows[i] >= committed) return fail(CV_ERR_INVALID, "row %lld out of range [0, %lld)", (long long)rows[i], (long long)committed);
+    std::lock_guard<std::mutex> wg(idx->upsert_mu);
+    int64_t i = 0;
+    while (i < n) {  // copy maximal contiguous runs
+        int64_t j = i + 1;
+        while (j < n && rows[j] == rows[j - 1] + 1) ++j;
+        const int64_t r0 = rows[i], m = j - i;
+        if (out_bf16)
+            CV_CUDA(cudaMemcpy2D(out_bf16 + i * idx->D, sizeof(uint16_t) * idx->D,
+                                 idx->E.ptr<uint16_t>() + r0 * idx->Dp, sizeof(uint16_t) * idx->Dp,
+                                 sizeof(uint16_t) * idx->D, m, cudaMemcpyDeviceToHost));
+        if (out_scale) CV_CUDA(cudaMemcpy(out_scale + i, idx->scale.ptr<float>() + r0, sizeof(float) * m, cudaMemcpyDeviceToHost));
+        if (out_ns) CV_CUDA(cudaMemcpy(out_ns + i, idx->ns.ptr<uint32_t>() + r0, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost));
+        if (out_label) CV_CUDA(cudaMemcpy(out_label + i, idx->label.ptr<uint32_t>() + r0, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost));
+        i = j;
+    }
+    return CV_OK;
+}
+
+int cv_stats(cv_index* idx, cv_stats_t* out) {
+    if (!idx || !out) return fail(CV_ERR_INVALID, "null argument");
+    memset(out, 0, sizeof(*out));
+    out->rows = idx->n_committed.load(std::memory_order_acquire);
+    out->capacity_rows = idx->capacity_rows;
+    out->bytes_per_row = 2ll * idx->Dp + 12;
+    out->queries = idx->queries.load();
+    out->kernel_launches = idx->launches.load();
+    out->upserted_rows = idx->upserted.load();
+    out->dim_padded = idx->Dp;
+    std::lock_guard<std::mutex> g(idx->stats_mu);
+    out->last_path = idx->last_path;
+    out->last_query_bytes = idx->last_bytes;
+    if (idx->last_timed && idx->last_timed->timed) {
+        DeviceGuard dg(idx->cfg.device);
+        float ms = 0.0f;
+        if (cudaEventSynchronize(idx->last_timed->t1) == cudaSuccess &&
+            cudaEventElapsedTime(&ms, idx->last_timed->t0, idx->last_timed->t1) == cudaSuccess)
+            out->last_query_ms = ms;
+        else
+            (void)cudaGetLastError();
+    }
+    return CV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,160 @@
+// common.cuh -- shared device utilities for the coddvec kernels (sm_100a).
+//
+// Result keys: u64 = ordered(score) << 32 | (0xFFFFFFFF - global_row).  Unsigned order of keys
+// == (score descending, row ascending) -- the tie rule of SURVEY.md section 8(c) -- so every
+// top-k / merge in this library is "k largest u64".  Key 0 is the empty slot.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cv {
+
+constexpr int kMaxK = 128;
+constexpr uint32_t kAny = 0xFFFFFFFFu;
+constexpr uint32_t kFullMask = 0xFFFFFFFFu;
+
+__host__ __device__ __forceinline__ uint32_t f32_bits(float f) {
+#ifdef __CUDA_ARCH__
+    return __float_as_uint(f);
+#else
+    union { float f; uint32_t u; } c; c.f = f; return c.u;
+#endif
+}
+__host__ __device__ __forceinline__ float bits_f32(uint32_t u) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    union { float f; uint32_t u; } c; c.u = u; return c.f;
+#endif
+}
+
+__host__ __device__ __forceinline__ uint64_t pack_key(float s, uint32_t row) {
+    if (!(s == s)) s = bits_f32(0xFF800000u);  // NaN -> -inf
+    s = s + 0.0f;                              // -0 -> +0
+    uint32_t u = f32_bits(s);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return (static_cast<uint64_t>(u) << 32) | static_cast<uint64_t>(0xFFFFFFFFu - row);
+}
+__host__ __device__ __forceinline__ float key_score(uint64_t key) {
+    uint32_t u = static_cast<uint32_t>(key >> 32);
+    u = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+    return bits_f32(u);
+}
+__host__ __device__ __forceinline__ uint32_t key_row(uint64_t key) {
+    return 0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull);
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float bf16lo_f32(uint32_t packed) { return __uint_as_float(packed << 16); }
+__device__ __forceinline__ float bf16hi_f32(uint32_t packed) { return __uint_as_float(packed & 0xFFFF0000u); }
+
+// streaming 16-byte load: read-only path, do not allocate in L1 (corpus rows are read once).
+__device__ __forceinline__ uint4 ldg_stream(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src) {
+    uint32_t lo = __shfl_sync(kFullMask, static_cast<uint32_t>(v), src);
+    uint32_t hi = __shfl_sync(kFullMask, static_cast<uint32_t>(v >> 32), src);
+    return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warp-parallel insertion into a descending k-list held in shared memory (empty slots = 0).
+// All 32 lanes call with the same (list, k, key).  Returns the new k-th entry (the threshold).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t warp_list_insert(uint64_t* list, int k, uint64_t key, int lane) {
+    uint64_t kth = list[k - 1];
+    if (key <= kth) return kth;
+    uint64_t v[kMaxK / 32];
+    int pos = 0;
+#pragma unroll
+    for (int j = 0; j < kMaxK / 32; ++j) {
+        int i = j * 32 + lane;
+        v[j] = (i < k) ? list[i] : 0ull;
+        pos += __popc(__ballot_sync(kFullMask, v[j] > key));
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < kMaxK / 32; ++j) {
+        int i = j * 32 + lane;
+        if (i >= pos && i + 1 < k) list[i + 1] = v[j];
+    }
+    if (lane == 0) list[pos] = key;
+    __syncwarp();
+    return list[k - 1];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Block-wide bitonic sort (descending) of n = power of two u64 keys in shared memory.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void block_bitonic_desc(uint64_t* buf, int n) {
+    for (int size = 2; size <= n; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
+                int lo = 2 * t - (t & (stride - 1));
+                int hi = lo + stride;
+                bool desc = ((lo & size) == 0);
+                uint64_t a = buf[lo], b = buf[hi];
+                if ((a < b) == desc) { buf[lo] = b; buf[hi] = a; }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Block-wide streaming top-k selection over m candidate keys (any order, 0 = empty) read through
+// `src(i)`.  Exact.  The whole block must call it.  buf: shared scratch of kSelCap keys, cnt:
+// shared int.  On return buf[0..k) holds the k best keys descending (0 padded).
+//   tau: lower bound on the k-th best key (0 = none); candidates below it are dropped early.
+// Strategy: append survivors to buf; whenever fewer than blockDim.x free slots remain, sort buf,
+// keep the best k, and raise tau to the k-th.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSelCap = 2048;
+
+template <typename Src>
+__device__ __forceinline__ void block_select_topk(Src src, int m, int k, uint64_t tau, uint64_t* buf,
+                                                  int* cnt) {
+    __shared__ uint64_t s_tau;
+    __syncthreads();  // buf / cnt may still be in use by the caller's previous phase
+    if (threadIdx.x == 0) { *cnt = 0; s_tau = tau; }
+    __syncthreads();
+    int c = 0;  // block-uniform running count (tracked with __syncthreads_count, no re-read races)
+    for (int base = 0; base < m; base += blockDim.x) {
+        if (c > kSelCap - static_cast<int>(blockDim.x)) {
+            for (int i = c + threadIdx.x; i < kSelCap; i += blockDim.x) buf[i] = 0ull;
+            block_bitonic_desc(buf, kSelCap);
+            if (threadIdx.x == 0) {
+                int keep = 0;
+                while (keep < k && buf[keep] != 0ull) ++keep;
+                *cnt = keep;
+                if (keep == k && buf[k - 1] > s_tau) s_tau = buf[k - 1];
+            }
+            __syncthreads();
+            c = *cnt;
+            __syncthreads();
+        }
+        int i = base + threadIdx.x;
+        uint64_t key = (i < m) ? src(i) : 0ull;
+        const bool want = key != 0ull && key >= s_tau;
+        if (want) {
+            int p = atomicAdd(cnt, 1);
+            buf[p] = key;
+        }
+        c += __syncthreads_count(want);
+    }
+    int n = 32;
+    while (n < c || n < k) n <<= 1;  // c <= kSelCap, k <= kMaxK
+    __syncthreads();
+    for (int i = c + threadIdx.x; i < n; i += blockDim.x) buf[i] = 0ull;
+    block_bitonic_desc(buf, n);
+}
+#endif  // __CUDACC__
+
+}  // namespace cv

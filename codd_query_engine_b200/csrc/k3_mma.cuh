@@ -1,0 +1,39 @@
+// k3_mma.cuh -- interface of K3 `gemm_topk` (implementation in k3_mma.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <atomic>
+#include <string>
+
+namespace cv {
+
+struct MmaScratch {  // device scratch owned by the query context, grown on demand
+    unsigned char* p = nullptr;
+    size_t cap = 0;
+};
+
+struct MmaArgs {
+    const void* E;          // [n][Dp] bf16
+    const float* scale;
+    const uint32_t* ns;
+    const uint32_t* label;
+    const uint32_t* mask;
+    uint32_t ns_code, label_code;
+    int64_t n;
+    int D, Dp;
+    bool cosine;
+    uint32_t row_offset;
+    const float* q;         // [B][D] fp32 raw (device)
+    int B, k;
+    uint64_t* out;          // [B][k]
+    unsigned int* counter;
+    int sm_count;
+    cudaStream_t stream;
+};
+
+bool mma_supported(int Dp);
+// returns 0 or a CV_ERR_* code; text in mma_error().  *launches is incremented per kernel launch.
+int mma_enqueue(const MmaArgs& a, MmaScratch& scratch, std::atomic<int64_t>* launches);
+std::string& mma_error();
+
+}  // namespace cv

@@ -1,0 +1,280 @@
+"""ctypes binding of libcoddvec.so (include/coddvec.h).
+
+This is the only way the package computes anything: there is no CPU fallback.  If the shared
+library is missing or no B200 is visible, every compute call raises ``NativeError``.
+
+The boundary mirrors what the reference's chromadb collection object does for
+codd_dal/metrics/metrics_semantic_metadata_store.py:236-238 (upsert), :260 (get) and :314-316
+(query); id strings, documents and metadata stay in Python (collection.py).
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+from pathlib import Path
+
+import numpy as np
+
+CV_OK = 0
+CV_ERR_INVALID = -1
+CV_ERR_CUDA = -2
+CV_ERR_OOM = -3
+CV_ERR_NONFINITE = -4
+CV_ERR_UNSUPPORTED = -5
+
+METRIC_COSINE = 0
+METRIC_IP = 1
+ANY = 0xFFFFFFFF
+MAX_K = 128
+MAX_DIM = 4096
+
+PATH_AUTO = 0
+PATH_SCAN = 1
+PATH_MMA = 2
+
+LIB_NAME = "libcoddvec.so"
+
+
+class NativeError(RuntimeError):
+    """libcoddvec.so reported a failure (or is missing)."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"coddvec error {code}: {message}")
+        self.code = code
+
+
+class _Config(ctypes.Structure):
+    _fields_ = [
+        ("dim", ctypes.c_int32),
+        ("metric", ctypes.c_int32),
+        ("device", ctypes.c_int32),
+        ("flags", ctypes.c_int32),
+        ("capacity_rows", ctypes.c_int64),
+        ("max_rows", ctypes.c_int64),
+        ("row_offset", ctypes.c_int64),
+    ]
+
+
+class _QueryParams(ctypes.Structure):
+    _fields_ = [
+        ("n_queries", ctypes.c_int32),
+        ("k", ctypes.c_int32),
+        ("ns_code", ctypes.c_uint32),
+        ("label_code", ctypes.c_uint32),
+        ("mask", ctypes.c_void_p),
+        ("path", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+    ]
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [
+        ("rows", ctypes.c_int64),
+        ("capacity_rows", ctypes.c_int64),
+        ("bytes_per_row", ctypes.c_int64),
+        ("queries", ctypes.c_int64),
+        ("kernel_launches", ctypes.c_int64),
+        ("upserted_rows", ctypes.c_int64),
+        ("last_query_ms", ctypes.c_double),
+        ("last_query_bytes", ctypes.c_int64),
+        ("last_path", ctypes.c_int32),
+        ("dim_padded", ctypes.c_int32),
+    ]
+
+
+_lib = None
+
+
+def library_path() -> Path:
+    override = os.environ.get("CODDVEC_LIB")
+    return Path(override) if override else Path(__file__).resolve().parent / LIB_NAME
+
+
+def load_library() -> ctypes.CDLL:
+    """dlopen libcoddvec.so and declare every prototype of include/coddvec.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not path.exists():
+        raise NativeError(
+            CV_ERR_CUDA,
+            f"{path} not found: build it with `python -m codd_query_engine_b200.build` "
+            "(there is no CPU fallback)",
+        )
+    lib = ctypes.CDLL(str(path))
+    vp, i32, i64, u32, u64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32, ctypes.c_uint64
+    protos = {
+        "cv_create": (ctypes.c_int, [ctypes.POINTER(_Config), ctypes.POINTER(vp)]),
+        "cv_destroy": (None, [vp]),
+        "cv_upsert": (ctypes.c_int, [vp, vp, vp, vp, vp, i64, vp]),
+        "cv_upsert_device": (ctypes.c_int, [vp, vp, vp, vp, vp, i64, vp]),
+        "cv_query": (ctypes.c_int, [vp, vp, ctypes.POINTER(_QueryParams), vp, vp, vp]),
+        "cv_query_device": (ctypes.c_int, [vp, vp, ctypes.POINTER(_QueryParams), vp, vp]),
+        "cv_merge_keys_device": (ctypes.c_int, [i32, vp, i32, i32, i32, i32, vp, vp]),
+        "cv_decode_keys": (None, [vp, i64, vp, vp]),
+        "cv_encode_key": (u64, [ctypes.c_float, u32]),
+        "cv_get_rows": (ctypes.c_int, [vp, vp, i64, vp, vp, vp, vp]),
+        "cv_count": (i64, [vp]),
+        "cv_dim": (i32, [vp]),
+        "cv_set_profiling": (ctypes.c_int, [vp, i32]),
+        "cv_stats": (ctypes.c_int, [vp, ctypes.POINTER(Stats)]),
+        "cv_synchronize": (ctypes.c_int, [vp]),
+        "cv_last_error": (ctypes.c_char_p, []),
+        "cv_version": (ctypes.c_char_p, []),
+    }
+    for name, (res, args) in protos.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = (
+    "cv_create", "cv_destroy", "cv_upsert", "cv_upsert_device", "cv_query", "cv_query_device",
+    "cv_merge_keys_device", "cv_decode_keys", "cv_encode_key", "cv_get_rows", "cv_count", "cv_dim",
+    "cv_set_profiling", "cv_stats", "cv_synchronize", "cv_last_error", "cv_version",
+)
+
+
+def _check(rc: int) -> None:
+    if rc != CV_OK:
+        msg = load_library().cv_last_error().decode("utf-8", "replace")
+        if rc == CV_ERR_INVALID:
+            raise ValueError(f"coddvec: {msg}")
+        if rc == CV_ERR_NONFINITE:
+            raise ValueError(f"coddvec: {msg}")
+        if rc == CV_ERR_OOM:
+            raise MemoryError(f"coddvec: {msg}")
+        raise NativeError(rc, msg)
+
+
+def _ptr(a) -> ctypes.c_void_p:
+    return None if a is None else ctypes.c_void_p(a.ctypes.data)
+
+
+def decode_keys(keys: np.ndarray):
+    """u64 result keys -> (scores fp32, global rows int64, -1 = empty)."""
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    scores = np.empty(keys.shape, dtype=np.float32)
+    rows = np.empty(keys.shape, dtype=np.int64)
+    load_library().cv_decode_keys(_ptr(keys), keys.size, _ptr(scores), _ptr(rows))
+    return scores, rows
+
+
+def encode_key(score: float, row: int) -> int:
+    return int(load_library().cv_encode_key(float(score), int(row)))
+
+
+def merge_keys_device(device: int, keys_in_ptr: int, G: int, B: int, k_in: int, k_out: int, out_ptr: int,
+                      stream: int = 0) -> None:
+    """K4 on device pointers (e.g. torch tensors' data_ptr()) -- used after the NCCL all-gather."""
+    _check(load_library().cv_merge_keys_device(device, keys_in_ptr, G, B, k_in, k_out, out_ptr, stream or None))
+
+
+class NativeIndex:
+    """One device-resident shard: bf16 rows + scale + namespace/label codes on one B200."""
+
+    def __init__(self, dim: int, metric: int = METRIC_COSINE, device: int = 0, capacity_rows: int = 0,
+                 max_rows: int = 0, row_offset: int = 0):
+        self._lib = load_library()
+        self._h = ctypes.c_void_p()
+        cfg = _Config(int(dim), int(metric), int(device), 0, int(capacity_rows), int(max_rows), int(row_offset))
+        _check(self._lib.cv_create(ctypes.byref(cfg), ctypes.byref(self._h)))
+        self.dim = int(dim)
+        self.metric = int(metric)
+        self.device = int(device)
+        self.row_offset = int(row_offset)
+
+    # -- lifecycle
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.cv_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self) -> int:
+        return int(self._lib.cv_count(self._h))
+
+    count = __len__
+
+    # -- K1
+    def upsert(self, embeddings: np.ndarray, rows=None, ns_codes=None, label_codes=None) -> np.ndarray:
+        emb = np.ascontiguousarray(embeddings, dtype=np.float32)
+        if emb.ndim != 2 or emb.shape[1] != self.dim:
+            raise ValueError(f"embeddings must be [n][{self.dim}], got {emb.shape}")
+        n = emb.shape[0]
+        r = None if rows is None else np.ascontiguousarray(rows, dtype=np.int64)
+        ns = None if ns_codes is None else np.ascontiguousarray(ns_codes, dtype=np.uint32)
+        lb = None if label_codes is None else np.ascontiguousarray(label_codes, dtype=np.uint32)
+        for name, arr in (("rows", r), ("ns_codes", ns), ("label_codes", lb)):
+            if arr is not None and arr.shape != (n,):
+                raise ValueError(f"{name} must have shape ({n},)")
+        out = np.empty(n, dtype=np.int64)
+        _check(self._lib.cv_upsert(self._h, _ptr(r), _ptr(emb), _ptr(ns), _ptr(lb), n, _ptr(out)))
+        return out
+
+    def upsert_device(self, emb_ptr: int, n: int, rows=None, ns_ptr: int = 0, label_ptr: int = 0) -> np.ndarray:
+        """Embeddings already on this device ([n][dim] fp32, e.g. a torch tensor's data_ptr())."""
+        r = None if rows is None else np.ascontiguousarray(rows, dtype=np.int64)
+        out = np.empty(n, dtype=np.int64)
+        _check(self._lib.cv_upsert_device(self._h, _ptr(r), emb_ptr, ns_ptr or None, label_ptr or None, n, _ptr(out)))
+        return out
+
+    # -- K2 / K3 / K4
+    def query(self, queries: np.ndarray, k: int, ns_code: int = ANY, label_code: int = ANY, mask=None,
+              path: int = PATH_AUTO):
+        """Host API.  Returns (scores [B][k] fp32 desc, rows [B][k] int64 global (-1 pad), counts [B])."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise ValueError(f"queries must be [B][{self.dim}], got {q.shape}")
+        B = q.shape[0]
+        m = None
+        if mask is not None:
+            m = np.ascontiguousarray(mask, dtype=np.uint32)
+            need = (len(self) + 31) // 32
+            if m.ndim != 1 or m.shape[0] < need:
+                raise ValueError(f"mask needs {need} uint32 words, got shape {m.shape}")
+        p = _QueryParams(B, int(k), int(ns_code), int(label_code), None if m is None else m.ctypes.data, int(path), 0)
+        scores = np.empty((B, int(k) if k > 0 else 0), dtype=np.float32)
+        rows = np.empty((B, int(k) if k > 0 else 0), dtype=np.int64)
+        counts = np.empty(B, dtype=np.int32)
+        _check(self._lib.cv_query(self._h, _ptr(q), ctypes.byref(p), _ptr(scores), _ptr(rows), _ptr(counts)))
+        return scores, rows, counts
+
+    def query_device(self, q_ptr: int, B: int, k: int, out_keys_ptr: int, ns_code: int = ANY, label_code: int = ANY,
+                     mask_ptr: int = 0, path: int = PATH_AUTO, stream: int = 0) -> None:
+        """Asynchronous device-resident API: enqueue on `stream` (0 = the index's own), no sync."""
+        p = _QueryParams(int(B), int(k), int(ns_code), int(label_code), mask_ptr or None, int(path), 0)
+        _check(self._lib.cv_query_device(self._h, q_ptr, ctypes.byref(p), out_keys_ptr, stream or None))
+
+    # -- readback / bookkeeping
+    def get_rows(self, rows, want_vectors: bool = True):
+        r = np.ascontiguousarray(rows, dtype=np.int64)
+        n = r.shape[0]
+        vec = np.empty((n, self.dim), dtype=np.uint16) if want_vectors else None
+        scale = np.empty(n, dtype=np.float32)
+        ns = np.empty(n, dtype=np.uint32)
+        lb = np.empty(n, dtype=np.uint32)
+        _check(self._lib.cv_get_rows(self._h, _ptr(r), n, _ptr(vec), _ptr(scale), _ptr(ns), _ptr(lb)))
+        return vec, scale, ns, lb
+
+    def set_profiling(self, enabled: bool) -> None:
+        _check(self._lib.cv_set_profiling(self._h, 1 if enabled else 0))
+
+    def stats(self) -> Stats:
+        s = Stats()
+        _check(self._lib.cv_stats(self._h, ctypes.byref(s)))
+        return s
+
+    def synchronize(self) -> None:
+        _check(self._lib.cv_synchronize(self._h))
