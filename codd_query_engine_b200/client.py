@@ -1,0 +1,493 @@
+"""chromadb-compatible client object backed by the B200-native index (libcoddvec.so).
+
+This is the drop-in boundary of SURVEY.md section 8(b): the reference's
+``MetricsSemanticMetadataStore`` (codd_dal/metrics/metrics_semantic_metadata_store.py:43-75) is
+constructed with a duck-typed chromadb client and issues exactly
+
+    client.get_or_create_collection(name=..., metadata={"hnsw:space": "cosine", ...})   (:60-69)
+    collection.upsert(documents=[...], metadatas=[...], ids=[...])                       (:236-238)
+    collection.get(ids=[...])                                                            (:260)
+    collection.query(query_texts=[...], n_results=n)                                     (:314-316)
+    client.heartbeat()                       (codd_jobs/metrics_semantic_indexer_main.py:215, :330)
+
+``Client`` / ``Collection`` below answer those calls with chromadb's result shapes and conventions
+(ascending cosine *distance* = 1 - cos; nested per-query lists; upsert replaces; fewer rows than
+``n_results`` returns what exists; empty collection returns ``ids == [[]]``), plus the real chromadb
+kwargs the benchmarks need (``embeddings=``, ``query_embeddings=``, ``where=``, ``include=``,
+multi-query batches, ``count()``).  Vectors live on the GPU; id strings, documents and metadata stay
+here on the host, exactly the split chromadb makes between hnswlib and SQLite.
+
+There is no CPU path: every upsert / query goes through ``native.NativeIndex`` and raises if the CUDA
+library or a B200 is missing.
+"""
+
+from __future__ import annotations
+
+import threading
+import time
+import uuid
+from typing import Any, Callable, Optional, Sequence
+
+import numpy as np
+
+from . import native
+from .embedding import default_embedding_function
+from .native import NativeIndex
+from .where import ANY, compile_where, evaluate, validate_where
+
+DEFAULT_LABEL_FIELD = "category"
+_QUERY_INCLUDE = ("metadatas", "documents", "distances")
+_GET_INCLUDE = ("metadatas", "documents")
+_VALID_INCLUDE = {"metadatas", "documents", "distances", "embeddings", "uris", "data"}
+
+
+class DuplicateIDError(ValueError):
+    """Same id twice in one add/upsert call (chromadb.errors.DuplicateIDError)."""
+
+
+class NotFoundError(ValueError):
+    """Collection does not exist (chromadb.errors.NotFoundError)."""
+
+
+def _space_to_metric(metadata: Optional[dict]) -> int:
+    # chromadb's own default space is l2; the reference always asks for cosine
+    # (metrics_semantic_metadata_store.py:64).  An exact-scan l2 is not built, so cosine is the default here.
+    space = (metadata or {}).get("hnsw:space", "cosine")
+    if space == "cosine":
+        return native.METRIC_COSINE
+    if space == "ip":
+        return native.METRIC_IP
+    raise ValueError(f"hnsw:space={space!r} is not supported (cosine and ip only)")
+
+
+def _as_list(x) -> list:
+    if x is None:
+        return []
+    if isinstance(x, (str, bytes, dict)):
+        return [x]
+    return list(x)
+
+
+class Collection:
+    """One named collection: a device-resident vector shard + host-side id/metadata/document tables."""
+
+    def __init__(self, name: str, metadata: Optional[dict] = None,
+                 embedding_function: Optional[Callable[[Sequence[str]], Any]] = None, device: int = 0,
+                 capacity_rows: int = 0, max_rows: int = 0):
+        self.name = name
+        self.id = uuid.uuid4()
+        self.metadata = dict(metadata) if metadata else None
+        self._metric = _space_to_metric(metadata)
+        self._embed = embedding_function or default_embedding_function()
+        self._device = int((metadata or {}).get("coddvec:device", device))
+        self._label_field = str((metadata or {}).get("coddvec:label_field", DEFAULT_LABEL_FIELD))
+        self._capacity_rows = int((metadata or {}).get("coddvec:capacity_rows", capacity_rows))
+        self._max_rows = int((metadata or {}).get("coddvec:max_rows", max_rows))
+        self._lock = threading.RLock()
+        self._index: Optional[NativeIndex] = None  # created on first upsert (dimension inferred, like chromadb)
+        self._row_of: dict[str, int] = {}
+        self._ids: list[Optional[str]] = []
+        self._metadatas: list[Optional[dict]] = []
+        self._documents: list[Optional[str]] = []
+        self._alive = np.zeros(0, dtype=bool)
+        self._free_rows: list[int] = []
+        self._ns_codes: dict[Any, int] = {}
+        self._label_codes: dict[Any, int] = {}
+
+    # ------------------------------------------------------------------ helpers
+    def _ensure_index(self, dim: int) -> NativeIndex:
+        if self._index is None:
+            self._index = NativeIndex(dim, metric=self._metric, device=self._device,
+                                      capacity_rows=self._capacity_rows, max_rows=self._max_rows)
+        elif self._index.dim != dim:
+            raise ValueError(f"Embedding dimension {dim} does not match collection dimensionality {self._index.dim}")
+        return self._index
+
+    @staticmethod
+    def _code(table: dict, value) -> int:
+        # code 0 is "no value"; real values start at 1
+        if value is None or value == "":
+            return 0
+        code = table.get(value)
+        if code is None:
+            code = len(table) + 1
+            table[value] = code
+        return code
+
+    def _embed_texts(self, texts: Sequence[str]) -> np.ndarray:
+        out = np.asarray(self._embed(list(texts)), dtype=np.float32)
+        if out.ndim != 2 or out.shape[0] != len(texts):
+            raise ValueError(f"embedding function returned shape {out.shape} for {len(texts)} texts")
+        return out
+
+    @staticmethod
+    def _check_include(include, default):
+        inc = list(default) if include is None else list(include)
+        bad = [i for i in inc if i not in _VALID_INCLUDE]
+        if bad:
+            raise ValueError(f"include has unknown fields {bad}; allowed: {sorted(_VALID_INCLUDE)}")
+        return inc
+
+    @staticmethod
+    def _check_metadata(md) -> Optional[dict]:
+        if md is None:
+            return None
+        if not isinstance(md, dict):
+            raise ValueError(f"metadata must be a dict, got {type(md).__name__}")
+        for key, val in md.items():
+            if not isinstance(key, str):
+                raise ValueError("metadata keys must be str")
+            if not isinstance(val, (str, int, float, bool)) and val is not None:
+                raise ValueError(f"metadata value for {key!r} must be str, int, float or bool")
+        return dict(md)
+
+    # ------------------------------------------------------------------ writes
+    def _write(self, ids, embeddings, metadatas, documents, *, replace: bool) -> None:
+        ids = _as_list(ids)
+        n = len(ids)
+        if n == 0:
+            raise ValueError("ids must be a non-empty list")
+        if any(not isinstance(i, str) or not i for i in ids):
+            raise ValueError("ids must be non-empty strings")
+        if len(set(ids)) != n:
+            dup = sorted({i for i in ids if ids.count(i) > 1})
+            raise DuplicateIDError(f"Expected IDs to be unique, found duplicates of: {dup}")
+        documents = None if documents is None else _as_list(documents)
+        metadatas = None if metadatas is None else _as_list(metadatas)
+        for name, seq in (("documents", documents), ("metadatas", metadatas)):
+            if seq is not None and len(seq) != n:
+                raise ValueError(f"{name} has {len(seq)} entries for {n} ids")
+        if embeddings is None:
+            if documents is None:
+                raise ValueError("You must provide either embeddings or documents")
+            if any(not isinstance(d, str) for d in documents):
+                raise ValueError("documents must be strings")
+            emb = self._embed_texts(documents)
+        else:
+            emb = np.asarray(embeddings, dtype=np.float32)
+            if emb.ndim == 1:
+                emb = emb[None, :]
+            if emb.ndim != 2 or emb.shape[0] != n:
+                raise ValueError(f"embeddings has shape {emb.shape} for {n} ids")
+        mds = [self._check_metadata(m) for m in metadatas] if metadatas is not None else [None] * n
+
+        with self._lock:
+            if not replace:  # add(): existing ids are left untouched
+                keep = [j for j, i in enumerate(ids) if i not in self._row_of]
+                if not keep:
+                    return
+                if len(keep) != n:
+                    ids = [ids[j] for j in keep]
+                    emb = emb[keep]
+                    mds = [mds[j] for j in keep]
+                    documents = None if documents is None else [documents[j] for j in keep]
+                    n = len(ids)
+            index = self._ensure_index(emb.shape[1])
+            base = len(self._ids)
+            rows = np.empty(n, dtype=np.int64)
+            fresh = 0
+            for j, doc_id in enumerate(ids):
+                r = self._row_of.get(doc_id)
+                if r is None and self._free_rows:
+                    r = self._free_rows.pop()  # reuse a tombstoned row
+                if r is None:
+                    r = -1
+                    fresh += 1
+                rows[j] = r
+            ns = np.fromiter((self._code(self._ns_codes, (m or {}).get("namespace")) for m in mds), dtype=np.uint32, count=n)
+            lb = np.fromiter((self._code(self._label_codes, (m or {}).get(self._label_field)) for m in mds),
+                             dtype=np.uint32, count=n)
+            got = index.upsert(emb, rows=rows, ns_codes=ns, label_codes=lb)
+            if fresh:
+                grow = base + fresh - len(self._ids)
+                self._ids.extend([None] * grow)
+                self._metadatas.extend([None] * grow)
+                self._documents.extend([None] * grow)
+                self._alive = np.concatenate([self._alive, np.zeros(grow, dtype=bool)])
+            for j, doc_id in enumerate(ids):
+                r = int(got[j])
+                self._row_of[doc_id] = r
+                self._ids[r] = doc_id
+                self._metadatas[r] = mds[j]
+                self._documents[r] = None if documents is None else documents[j]
+                self._alive[r] = True
+
+    def upsert(self, ids, embeddings=None, metadatas=None, documents=None, **_ignored) -> None:
+        """Insert-or-replace by id (vector, document and metadata are all replaced)."""
+        self._write(ids, embeddings, metadatas, documents, replace=True)
+
+    def add(self, ids, embeddings=None, metadatas=None, documents=None, **_ignored) -> None:
+        """Insert; ids that already exist are left untouched (chromadb logs and skips them)."""
+        self._write(ids, embeddings, metadatas, documents, replace=False)
+
+    def update(self, ids, embeddings=None, metadatas=None, documents=None, **_ignored) -> None:
+        """Update existing ids only; unknown ids are ignored."""
+        ids = _as_list(ids)
+        with self._lock:
+            known = [j for j, i in enumerate(ids) if i in self._row_of]
+            if not known:
+                return
+            pick = lambda seq: None if seq is None else [_as_list(seq)[j] for j in known]  # noqa: E731
+            sub_ids = [ids[j] for j in known]
+            docs, mds = pick(documents), pick(metadatas)
+            if embeddings is None and docs is None:
+                for j, doc_id in enumerate(sub_ids):  # metadata-only update keeps the vector
+                    r = self._row_of[doc_id]
+                    if mds is not None:
+                        merged = dict(self._metadatas[r] or {})
+                        merged.update(self._check_metadata(mds[j]) or {})
+                        self._metadatas[r] = merged
+                return
+            emb = None if embeddings is None else np.asarray(embeddings, dtype=np.float32)[known]
+            if mds is None:
+                mds = [self._metadatas[self._row_of[i]] for i in sub_ids]
+            if docs is None:
+                docs = [self._documents[self._row_of[i]] for i in sub_ids]
+            self._write(sub_ids, emb, mds, docs, replace=True)
+
+    def delete(self, ids=None, where=None, **_ignored) -> None:
+        """Tombstone rows; their slots are reused by later inserts and masked out of queries."""
+        with self._lock:
+            if ids is None and where is None:
+                raise ValueError("delete needs ids or where")
+            targets = [self._row_of[i] for i in _as_list(ids) if i in self._row_of] if ids is not None else \
+                [r for r in range(len(self._ids)) if self._alive[r]]
+            if where is not None:
+                validate_where(where)
+                targets = [r for r in targets if evaluate(where, self._metadatas[r])]
+            for r in targets:
+                self._row_of.pop(self._ids[r], None)
+                self._ids[r] = None
+                self._metadatas[r] = None
+                self._documents[r] = None
+                self._alive[r] = False
+                self._free_rows.append(r)
+
+    # ------------------------------------------------------------------ reads
+    def count(self) -> int:
+        with self._lock:
+            return len(self._row_of)
+
+    def _rows_result(self, rows: Sequence[int], include) -> dict:
+        out = {"ids": [self._ids[r] for r in rows], "embeddings": None, "metadatas": None, "documents": None,
+               "uris": None, "data": None, "included": list(include)}
+        if "metadatas" in include:
+            out["metadatas"] = [dict(self._metadatas[r]) if self._metadatas[r] is not None else None for r in rows]
+        if "documents" in include:
+            out["documents"] = [self._documents[r] for r in rows]
+        if "embeddings" in include:
+            out["embeddings"] = self._stored_vectors(rows)
+        return out
+
+    def _stored_vectors(self, rows: Sequence[int]) -> np.ndarray:
+        """What the device holds for `rows` (bf16 of the normalised input), widened to fp32."""
+        if self._index is None or len(rows) == 0:
+            return np.zeros((0, self._index.dim if self._index else 0), dtype=np.float32)
+        vec, _, _, _ = self._index.get_rows(np.asarray(rows, dtype=np.int64))
+        return (vec.astype(np.uint32) << np.uint32(16)).view(np.float32)
+
+    def get(self, ids=None, where=None, limit: Optional[int] = None, offset: Optional[int] = None, include=None,
+            **_ignored) -> dict:
+        include = self._check_include(include, _GET_INCLUDE)
+        with self._lock:
+            if ids is not None:
+                rows = [self._row_of[i] for i in _as_list(ids) if i in self._row_of]
+            else:
+                rows = [r for r in range(len(self._ids)) if self._alive[r]]
+            if where is not None:
+                validate_where(where)
+                rows = [r for r in rows if evaluate(where, self._metadatas[r])]
+            if offset:
+                rows = rows[int(offset):]
+            if limit is not None:
+                rows = rows[:int(limit)]
+            return self._rows_result(rows, include)
+
+    def peek(self, limit: int = 10) -> dict:
+        return self.get(limit=limit, include=["metadatas", "documents", "embeddings"])
+
+    def query(self, query_embeddings=None, query_texts=None, n_results: int = 10, where=None, include=None,
+              **_ignored) -> dict:
+        """Exact cosine / inner-product top-k.  Results per query ascend by distance = 1 - score."""
+        include = self._check_include(include, _QUERY_INCLUDE)
+        if (query_embeddings is None) == (query_texts is None):
+            raise ValueError("You must provide exactly one of query_embeddings or query_texts")
+        if int(n_results) < 1:
+            raise ValueError(f"Number of requested results {n_results}, cannot be negative, or zero.")
+        if query_texts is not None:
+            texts = _as_list(query_texts)
+            if not texts or any(not isinstance(t, str) for t in texts):
+                raise ValueError("query_texts must be a non-empty list of strings")
+            q = self._embed_texts(texts)
+        else:
+            q = np.asarray(query_embeddings, dtype=np.float32)
+            if q.ndim == 1:
+                q = q[None, :]
+            if q.ndim != 2 or q.shape[0] == 0:
+                raise ValueError(f"query_embeddings has shape {q.shape}")
+        B = q.shape[0]
+
+        def empty():
+            res = {"ids": [[] for _ in range(B)], "embeddings": None, "distances": None, "metadatas": None,
+                   "documents": None, "uris": None, "data": None, "included": list(include)}
+            for field in ("distances", "metadatas", "documents", "embeddings"):
+                if field in include:
+                    res[field] = [[] for _ in range(B)]
+            return res
+
+        with self._lock:
+            if self._index is None or not self._row_of:
+                return empty()
+            if q.shape[1] != self._index.dim:
+                raise ValueError(f"Embedding dimension {q.shape[1]} does not match collection dimensionality {self._index.dim}")
+            compiled = compile_where(where, self._metadatas, self._ns_codes, self._label_field, self._label_codes,
+                                     alive=self._alive if self._free_rows else None)
+            if compiled.empty:
+                return empty()
+            k = min(int(n_results), native.MAX_K, len(self._row_of))
+            scores, rows, counts = self._index.query(q, k, ns_code=compiled.ns_code, label_code=compiled.label_code,
+                                                     mask=compiled.mask_words)
+            if self._metric == native.METRIC_COSINE:
+                np.clip(scores, -1.0, 1.0, out=scores)
+            res = empty()
+            for b in range(B):
+                hit = [int(r) for r in rows[b, : int(counts[b])]]
+                res["ids"][b] = [self._ids[r] for r in hit]
+                if "distances" in include:
+                    res["distances"][b] = [float(np.float32(1.0) - s) for s in scores[b, : len(hit)]]
+                if "metadatas" in include:
+                    res["metadatas"][b] = [dict(self._metadatas[r]) if self._metadatas[r] is not None else None for r in hit]
+                if "documents" in include:
+                    res["documents"][b] = [self._documents[r] for r in hit]
+                if "embeddings" in include:
+                    res["embeddings"][b] = self._stored_vectors(hit)
+            return res
+
+    def modify(self, name: Optional[str] = None, metadata: Optional[dict] = None) -> None:
+        if name is not None:
+            self.name = name
+        if metadata is not None:
+            self.metadata = dict(metadata)
+
+    # ------------------------------------------------------------------ extras
+    def stats(self):
+        """Device-side counters (rows, launches, last query ms/bytes, path) -- SURVEY.md section 5."""
+        return None if self._index is None else self._index.stats()
+
+    def close(self) -> None:
+        with self._lock:
+            if self._index is not None:
+                self._index.close()
+                self._index = None
+
+
+class _Registry:
+    """Collections of one logical server (shared by every client that names the same endpoint)."""
+
+    def __init__(self):
+        self.lock = threading.RLock()
+        self.collections: dict[str, Collection] = {}
+
+
+_REGISTRIES: dict[Any, _Registry] = {}
+_REGISTRIES_LOCK = threading.Lock()
+
+
+def _registry(key) -> _Registry:
+    with _REGISTRIES_LOCK:
+        reg = _REGISTRIES.get(key)
+        if reg is None:
+            reg = _REGISTRIES[key] = _Registry()
+        return reg
+
+
+class Client:
+    """Duck-typed chromadb ClientAPI.  Clients naming the same endpoint share their collections,
+    as separate ``chromadb.HttpClient(host, port)`` objects pointed at one server do (the reference
+    service builds a fresh client per request: codd_service/.../metrics_controller.py:168)."""
+
+    def __init__(self, endpoint: Any = "ephemeral", device: int = 0,
+                 embedding_function: Optional[Callable] = None, **_ignored):
+        self._reg = _registry(endpoint)
+        self._device = int(device)
+        self._embedding_function = embedding_function
+        self.endpoint = endpoint
+
+    def heartbeat(self) -> int:
+        """Nanosecond timestamp; raises if the CUDA library cannot be loaded (there is nothing to serve without it)."""
+        native.load_library()
+        return time.time_ns()
+
+    def get_version(self) -> str:
+        return native.load_library().cv_version().decode()
+
+    def create_collection(self, name: str, metadata: Optional[dict] = None, embedding_function=None,
+                          get_or_create: bool = False, **_ignored) -> Collection:
+        if not isinstance(name, str) or not name:
+            raise ValueError("collection name must be a non-empty string")
+        with self._reg.lock:
+            existing = self._reg.collections.get(name)
+            if existing is not None:
+                if get_or_create:
+                    return existing
+                raise ValueError(f"Collection {name} already exists")
+            coll = Collection(name, metadata, embedding_function or self._embedding_function, device=self._device)
+            self._reg.collections[name] = coll
+            return coll
+
+    def get_or_create_collection(self, name: str, metadata: Optional[dict] = None, embedding_function=None,
+                                 **_ignored) -> Collection:
+        return self.create_collection(name, metadata, embedding_function, get_or_create=True)
+
+    def get_collection(self, name: str, embedding_function=None, **_ignored) -> Collection:
+        with self._reg.lock:
+            coll = self._reg.collections.get(name)
+            if coll is None:
+                raise NotFoundError(f"Collection {name} does not exist.")
+            return coll
+
+    def list_collections(self, limit: Optional[int] = None, offset: Optional[int] = None) -> list:
+        with self._reg.lock:
+            colls = list(self._reg.collections.values())
+        colls = colls[int(offset or 0):]
+        return colls if limit is None else colls[: int(limit)]
+
+    def count_collections(self) -> int:
+        with self._reg.lock:
+            return len(self._reg.collections)
+
+    def delete_collection(self, name: str) -> None:
+        with self._reg.lock:
+            coll = self._reg.collections.pop(name, None)
+        if coll is None:
+            raise NotFoundError(f"Collection {name} does not exist.")
+        coll.close()
+
+    def reset(self) -> bool:
+        with self._reg.lock:
+            colls = list(self._reg.collections.values())
+            self._reg.collections.clear()
+        for c in colls:
+            c.close()
+        return True
+
+
+ClientAPI = Client
+
+
+def EphemeralClient(**kwargs) -> Client:  # noqa: N802 - chromadb's factory names
+    return Client("ephemeral", **kwargs)
+
+
+def HttpClient(host: str = "localhost", port: int = 8000, **kwargs) -> Client:  # noqa: N802
+    """In-process stand-in for ``chromadb.HttpClient(host, port)`` (codd_lib/.../promql_module.py:59-62,
+    codd_jobs/metrics_semantic_indexer_main.py:209-212): the "server" is this process's GPU."""
+    kwargs.pop("ssl", None)
+    kwargs.pop("headers", None)
+    kwargs.pop("settings", None)
+    return Client(("http", str(host), int(port)), **kwargs)
+
+
+def PersistentClient(path: str = "./chroma", **kwargs) -> Client:  # noqa: N802
+    kwargs.pop("settings", None)
+    return Client(("path", str(path)), **kwargs)

@@ -468,6 +468,7 @@ static int upsert_impl(cv_index* idx, const int64_t* rows, const float* emb, con
     DeviceGuard dg(idx->cfg.device);
     if (!dg.ok) return fail(CV_ERR_CUDA, "cudaSetDevice(%d) failed", idx->cfg.device);
     std::lock_guard<std::mutex> wg(idx->upsert_mu);
+    if (on_device) CV_CUDA(cudaDeviceSynchronize());  // whatever produced d_emb (any stream) must be done
 
     const int64_t committed = idx->n_committed.load(std::memory_order_acquire);
     // resolve destination rows: appends get committed, committed+1, ...

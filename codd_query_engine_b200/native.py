@@ -168,10 +168,23 @@ def encode_key(score: float, row: int) -> int:
     return int(load_library().cv_encode_key(float(score), int(row)))
 
 
+CUDA_STREAM_LEGACY = 1  # cudaStreamLegacy: the handle that names the default (NULL) stream explicitly
+
+
+def _stream_arg(stream):
+    """None -> the library's own stream; 0 (torch's default-stream handle) -> cudaStreamLegacy."""
+    if stream is None:
+        return None
+    return ctypes.c_void_p(CUDA_STREAM_LEGACY if int(stream) == 0 else int(stream))
+
+
 def merge_keys_device(device: int, keys_in_ptr: int, G: int, B: int, k_in: int, k_out: int, out_ptr: int,
-                      stream: int = 0) -> None:
-    """K4 on device pointers (e.g. torch tensors' data_ptr()) -- used after the NCCL all-gather."""
-    _check(load_library().cv_merge_keys_device(device, keys_in_ptr, G, B, k_in, k_out, out_ptr, stream or None))
+                      stream=0) -> None:
+    """K4 on device pointers (e.g. torch tensors' data_ptr()) -- used after the NCCL all-gather.
+
+    stream: a cudaStream_t handle (torch.cuda.current_stream().cuda_stream); 0/None = default stream."""
+    _check(load_library().cv_merge_keys_device(device, keys_in_ptr, G, B, k_in, k_out, out_ptr,
+                                               _stream_arg(0 if stream is None else stream)))
 
 
 class NativeIndex:
@@ -252,10 +265,13 @@ class NativeIndex:
         return scores, rows, counts
 
     def query_device(self, q_ptr: int, B: int, k: int, out_keys_ptr: int, ns_code: int = ANY, label_code: int = ANY,
-                     mask_ptr: int = 0, path: int = PATH_AUTO, stream: int = 0) -> None:
-        """Asynchronous device-resident API: enqueue on `stream` (0 = the index's own), no sync."""
+                     mask_ptr: int = 0, path: int = PATH_AUTO, stream=None) -> None:
+        """Asynchronous device-resident API: enqueue on `stream`, no sync.
+
+        stream: None = the index's own stream; otherwise a cudaStream_t handle such as
+        torch.cuda.current_stream().cuda_stream (0 = the default stream)."""
         p = _QueryParams(int(B), int(k), int(ns_code), int(label_code), mask_ptr or None, int(path), 0)
-        _check(self._lib.cv_query_device(self._h, q_ptr, ctypes.byref(p), out_keys_ptr, stream or None))
+        _check(self._lib.cv_query_device(self._h, q_ptr, ctypes.byref(p), out_keys_ptr, _stream_arg(stream)))
 
     # -- readback / bookkeeping
     def get_rows(self, rows, want_vectors: bool = True):

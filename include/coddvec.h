@@ -113,8 +113,8 @@ int cv_upsert_device(cv_index* idx, const int64_t* rows, const float* d_emb, con
 int cv_query(cv_index* idx, const float* q, const cv_query_params* p, float* out_scores,
              int64_t* out_rows, int32_t* out_counts);
 /* Asynchronous, device-resident variant: d_q [B][dim] fp32 and d_out_keys [B][k] u64 are device
- * memory; work is enqueued on `stream` (a cudaStream_t; NULL = the index's own stream) and NOT
- * synchronised. */
+ * memory; work is enqueued on `stream` (a cudaStream_t; NULL = the index's own stream; pass
+ * cudaStreamLegacy / cudaStreamPerThread to name a default stream) and NOT synchronised. */
 int cv_query_device(cv_index* idx, const float* d_q, const cv_query_params* p, uint64_t* d_out_keys,
                     void* stream);
 

@@ -1,0 +1,74 @@
+"""Test double for native.NativeIndex, backed by the CPU oracle.
+
+TEST INFRASTRUCTURE ONLY: lets the host-side logic of client.py / sharded.py run in the CPU-only
+container (`-m "not gpu"`).  The product never falls back to this: client.py always constructs
+native.NativeIndex, tests substitute the class with monkeypatch.
+"""
+import numpy as np
+
+from oracle import brute_force as bf
+
+
+class OracleIndex:
+    def __init__(self, dim, metric=bf.METRIC_COSINE, device=0, capacity_rows=0, max_rows=0, row_offset=0):
+        self.dim, self.metric, self.device, self.row_offset = int(dim), int(metric), int(device), int(row_offset)
+        self._stored = np.zeros((0, dim), np.uint16)
+        self._scale = np.zeros(0, np.float32)
+        self._ns = np.zeros(0, np.uint32)
+        self._label = np.zeros(0, np.uint32)
+        self.queries = 0
+
+    def __len__(self):
+        return self._stored.shape[0]
+
+    count = __len__
+
+    def close(self):
+        pass
+
+    def upsert(self, embeddings, rows=None, ns_codes=None, label_codes=None):
+        emb = np.ascontiguousarray(embeddings, dtype=np.float32)
+        if emb.ndim != 2 or emb.shape[1] != self.dim:
+            raise ValueError("bad embedding shape")
+        if not np.isfinite(emb).all():
+            raise ValueError("coddvec: embeddings contain NaN/Inf")
+        n = emb.shape[0]
+        rows = np.full(n, -1, np.int64) if rows is None else np.asarray(rows, np.int64)
+        stored, scale = bf.normalise_store(emb, self.metric)
+        ns = np.zeros(n, np.uint32) if ns_codes is None else np.asarray(ns_codes, np.uint32)
+        lb = np.zeros(n, np.uint32) if label_codes is None else np.asarray(label_codes, np.uint32)
+        out = np.empty(n, np.int64)
+        committed = len(self)
+        app = int((rows < 0).sum())
+        if (rows >= committed).any():
+            raise ValueError("coddvec: row is not committed")
+        self._stored = np.concatenate([self._stored, np.zeros((app, self.dim), np.uint16)])
+        self._scale = np.concatenate([self._scale, np.zeros(app, np.float32)])
+        self._ns = np.concatenate([self._ns, np.zeros(app, np.uint32)])
+        self._label = np.concatenate([self._label, np.zeros(app, np.uint32)])
+        nxt = committed
+        for i in range(n):
+            r = int(rows[i])
+            if r < 0:
+                r = nxt
+                nxt += 1
+            self._stored[r], self._scale[r], self._ns[r], self._label[r] = stored[i], scale[i], ns[i], lb[i]
+            out[i] = r
+        return out
+
+    def query(self, queries, k, ns_code=bf.ANY_CODE, label_code=bf.ANY_CODE, mask=None, path=0):
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        if not 1 <= k <= 128:
+            raise ValueError("coddvec: k must be in [1, 128]")
+        self.queries += 1
+        return bf.query(self._stored, self._scale, q, k, metric=self.metric, mask_words=mask, ns=self._ns,
+                        ns_code=ns_code, label=self._label, label_code=label_code, row_offset=self.row_offset)
+
+    def get_rows(self, rows, want_vectors=True):
+        r = np.asarray(rows, np.int64)
+        return self._stored[r], self._scale[r], self._ns[r], self._label[r]
+
+    def stats(self):
+        return None

@@ -1,0 +1,238 @@
+"""chromadb-compatible Client / Collection: conventions of SURVEY.md section 8(b) and the extensions
+(embeddings=, query_embeddings=, where=, include=, multi-query, count, delete).  Host logic runs on
+the CPU with the oracle-backed double; the same tests run on the GPU through libcoddvec.so."""
+import numpy as np
+import pytest
+
+from codd_query_engine_b200 import client as client_mod
+from codd_query_engine_b200.where import compile_where, evaluate, pack_mask, validate_where
+from oracle import brute_force as bf
+from tests.doubles import OracleIndex
+
+COSINE = {"hnsw:space": "cosine", "hnsw:construction_ef": 200, "hnsw:search_ef": 100, "hnsw:M": 16}
+
+
+@pytest.fixture(params=["double", pytest.param("native", marks=pytest.mark.gpu)])
+def client(request, monkeypatch):
+    if request.param == "double":
+        monkeypatch.setattr(client_mod, "NativeIndex", OracleIndex)
+    c = client_mod.Client(endpoint=("test", request.node.name))
+    yield c
+    c.reset()
+
+
+def vecs(n, d=384, seed=0):
+    return np.random.default_rng(seed).standard_normal((n, d)).astype(np.float32)
+
+
+def test_get_or_create_is_idempotent_and_isolated(client):
+    a = client.get_or_create_collection(name="a", metadata=COSINE)
+    assert client.get_or_create_collection(name="a", metadata=COSINE) is a
+    b = client.get_or_create_collection(name="b")
+    a.upsert(ids=["x"], embeddings=vecs(1))
+    assert a.count() == 1 and b.count() == 0
+    assert a.metadata == COSINE  # hnsw:* keys are accepted and echoed back
+    assert {c.name for c in client.list_collections()} == {"a", "b"}
+    with pytest.raises(ValueError):
+        client.create_collection("a")
+    client.delete_collection("b")
+    with pytest.raises(client_mod.NotFoundError):
+        client.get_collection("b")
+    assert isinstance(client.heartbeat(), int)
+
+
+def test_clients_naming_one_endpoint_share_collections(monkeypatch):
+    monkeypatch.setattr(client_mod, "NativeIndex", OracleIndex)
+    c1 = client_mod.HttpClient(host="localhost", port=8000)
+    c2 = client_mod.HttpClient(host="localhost", port=8000)
+    c3 = client_mod.HttpClient(host="localhost", port=8001)
+    c1.get_or_create_collection("shared").upsert(ids=["a"], embeddings=vecs(1))
+    assert c2.get_collection("shared").count() == 1
+    with pytest.raises(client_mod.NotFoundError):
+        c3.get_collection("shared")
+    c1.reset()
+
+
+def test_query_shapes_and_conventions(client):
+    coll = client.get_or_create_collection("c", metadata=COSINE)
+    empty = coll.query(query_embeddings=vecs(2, seed=9), n_results=3)
+    assert empty["ids"] == [[], []] and empty["distances"] == [[], []]
+    x = vecs(50)
+    ids = [f"ns#{i}" for i in range(50)]
+    coll.upsert(ids=ids, embeddings=x, metadatas=[{"namespace": "ns", "i": i} for i in range(50)],
+                documents=[f"doc {i}" for i in range(50)])
+    res = coll.query(query_embeddings=x[7:9], n_results=5)
+    assert [len(r) for r in res["ids"]] == [5, 5]
+    assert res["ids"][0][0] == "ns#7" and res["ids"][1][0] == "ns#8"
+    for b in range(2):
+        d = res["distances"][b]
+        assert all(d[i] <= d[i + 1] for i in range(4)) and abs(d[0]) < 1e-3  # ascending distance, self ~ 0
+        assert res["documents"][b][0] == f"doc {7 + b}" and res["metadatas"][b][0]["i"] == 7 + b
+    assert res["embeddings"] is None
+    # fewer rows than n_results -> what exists
+    assert len(coll.query(query_embeddings=x[:1], n_results=100)["ids"][0]) == 50
+    # include
+    only = coll.query(query_embeddings=x[:1], n_results=2, include=["distances"])
+    assert only["metadatas"] is None and only["documents"] is None and len(only["distances"][0]) == 2
+    emb = coll.query(query_embeddings=x[:1], n_results=2, include=["embeddings"])["embeddings"][0]
+    assert emb.shape == (2, 384) and abs(np.linalg.norm(emb[0]) - 1) < 1e-2
+    with pytest.raises(ValueError):
+        coll.query(query_embeddings=x[:1], n_results=0)
+    with pytest.raises(ValueError):
+        coll.query(query_embeddings=x[:1], query_texts=["both"])
+    with pytest.raises(ValueError):
+        coll.query(query_embeddings=vecs(1, d=100), n_results=1)
+
+
+def test_distances_match_oracle(client):
+    coll = client.get_or_create_collection("c", metadata=COSINE)
+    x, q = vecs(2000, seed=1), vecs(3, seed=2)
+    coll.upsert(ids=[str(i) for i in range(2000)], embeddings=x)
+    res = coll.query(query_embeddings=q, n_results=10)
+    stored, scale = bf.normalise_store(x)
+    s, r, c = bf.query(stored, scale, q, 10)
+    for b in range(3):
+        assert res["ids"][b] == [str(i) for i in r[b]]
+        assert np.allclose(res["distances"][b], 1 - s[b], atol=1e-5)
+
+
+def test_upsert_replaces_vector_document_and_metadata(client):
+    coll = client.get_or_create_collection("c", metadata=COSINE)
+    x = vecs(10)
+    coll.upsert(ids=[str(i) for i in range(10)], embeddings=x, documents=["old"] * 10, metadatas=[{"v": 1}] * 10)
+    coll.upsert(ids=["3"], embeddings=-x[3:4], documents=["new"], metadatas=[{"v": 2}])
+    assert coll.count() == 10
+    got = coll.get(ids=["3"])
+    assert got["ids"] == ["3"] and got["documents"] == ["new"] and got["metadatas"] == [{"v": 2}]
+    res = coll.query(query_embeddings=x[3:4], n_results=10)
+    assert res["ids"][0][-1] == "3" and res["distances"][0][-1] > 1.99  # now opposite to its old self
+    assert coll.get(ids=["nope"])["ids"] == []
+    with pytest.raises(client_mod.DuplicateIDError):
+        coll.upsert(ids=["a", "a"], embeddings=x[:2])
+    with pytest.raises(ValueError):
+        coll.upsert(ids=["a"], embeddings=vecs(1, d=8))
+
+
+def test_text_path_uses_embedding_function(client):
+    calls = []
+
+    def embed(texts):
+        calls.append(list(texts))
+        out = np.zeros((len(texts), 16), np.float32)
+        for i, t in enumerate(texts):
+            out[i, len(t) % 16] = 1.0
+        return out
+
+    coll = client.get_or_create_collection("c", metadata=COSINE, embedding_function=embed)
+    coll.upsert(ids=["a", "b"], documents=["xx", "yyy"])
+    res = coll.query(query_texts=["zz"], n_results=2)
+    assert res["ids"][0][0] == "a" and abs(res["distances"][0][0]) < 1e-6 and abs(res["distances"][0][1] - 1) < 1e-6
+    assert calls == [["xx", "yyy"], ["zz"]]
+    with pytest.raises(ValueError):
+        coll.upsert(ids=["c"])
+
+
+def test_where_filters(client):
+    coll = client.get_or_create_collection("c", metadata=COSINE)
+    n = 300
+    x = vecs(n, seed=3)
+    rng = np.random.default_rng(4)
+    ns = [f"ns{rng.integers(0, 3)}" for _ in range(n)]
+    cat = [["system", "app", "db"][rng.integers(0, 3)] for _ in range(n)]
+    lvl = rng.integers(0, 10, n).tolist()
+    coll.upsert(ids=[str(i) for i in range(n)], embeddings=x,
+                metadatas=[{"namespace": ns[i], "category": cat[i], "lvl": lvl[i]} for i in range(n)])
+    stored, scale = bf.normalise_store(x)
+    q = vecs(1, seed=5)
+    full = bf.scores_fp32(stored, scale, bf.normalise_query(q))[0]
+
+    def expect(pred, k=10):
+        el = np.array([pred(i) for i in range(n)])
+        order = [i for i in np.argsort(-full, kind="stable") if el[i]][:k]
+        return [str(i) for i in order]
+
+    cases = [
+        ({"namespace": "ns1"}, lambda i: ns[i] == "ns1"),
+        ({"namespace": {"$eq": "ns2"}}, lambda i: ns[i] == "ns2"),
+        ({"$and": [{"namespace": "ns0"}, {"category": "db"}]}, lambda i: ns[i] == "ns0" and cat[i] == "db"),
+        ({"lvl": {"$gte": 7}}, lambda i: lvl[i] >= 7),
+        ({"$and": [{"namespace": "ns1"}, {"lvl": {"$lt": 3}}]}, lambda i: ns[i] == "ns1" and lvl[i] < 3),
+        ({"$or": [{"category": "app"}, {"lvl": 0}]}, lambda i: cat[i] == "app" or lvl[i] == 0),
+        ({"category": {"$in": ["db", "app"]}}, lambda i: cat[i] in ("db", "app")),
+        ({"namespace": {"$ne": "ns0"}}, lambda i: ns[i] != "ns0"),
+    ]
+    for where, pred in cases:
+        got = coll.query(query_embeddings=q, n_results=10, where=where)["ids"][0]
+        assert got == expect(pred), where
+    assert coll.query(query_embeddings=q, n_results=10, where={"namespace": "missing"})["ids"] == [[]]
+    assert coll.query(query_embeddings=q, n_results=10, where={"lvl": {"$gt": 99}})["ids"] == [[]]
+    with pytest.raises(ValueError):
+        coll.query(query_embeddings=q, n_results=10, where={"$bogus": []})
+    assert len(coll.get(where={"namespace": "ns1"})["ids"]) == sum(1 for v in ns if v == "ns1")
+
+
+def test_delete_add_update(client):
+    coll = client.get_or_create_collection("c", metadata=COSINE)
+    x = vecs(20, seed=6)
+    coll.add(ids=[str(i) for i in range(20)], embeddings=x, metadatas=[{"i": i} for i in range(20)])
+    coll.add(ids=["5"], embeddings=-x[5:6])  # existing id: ignored
+    assert coll.query(query_embeddings=x[5:6], n_results=1)["ids"][0] == ["5"]
+    coll.delete(ids=["5", "6"])
+    assert coll.count() == 18 and coll.get(ids=["5"])["ids"] == []
+    top = coll.query(query_embeddings=x[5:6], n_results=20)["ids"][0]
+    assert len(top) == 18 and "5" not in top and "6" not in top
+    coll.upsert(ids=["new"], embeddings=x[5:6])  # reuses a tombstoned row
+    assert coll.count() == 19 and coll.query(query_embeddings=x[5:6], n_results=1)["ids"][0] == ["new"]
+    coll.update(ids=["7", "ghost"], metadatas=[{"tag": "t"}, {"tag": "u"}])
+    assert coll.get(ids=["7"])["metadatas"] == [{"i": 7, "tag": "t"}] and coll.count() == 19
+    coll.delete(where={"i": {"$lt": 3}})
+    assert coll.count() == 16
+    assert len(coll.peek(3)["ids"]) == 3
+
+
+def test_ip_space(client):
+    coll = client.get_or_create_collection("c", metadata={"hnsw:space": "ip"})
+    x = np.array([[1, 0, 0, 0], [2, 0, 0, 0], [0, 3, 0, 0]], np.float32)
+    coll.upsert(ids=["a", "b", "c"], embeddings=x)
+    res = coll.query(query_embeddings=[[1, 0, 0, 0]], n_results=3)
+    assert res["ids"][0] == ["b", "a", "c"] and res["distances"][0] == [-1.0, 0.0, 1.0]
+    with pytest.raises(ValueError):
+        client.get_or_create_collection("l2", metadata={"hnsw:space": "l2"})
+
+
+# ---------------------------------------------------------------- where compiler (pure host logic)
+def test_where_compiler_splits_fused_and_residual_predicates():
+    mds = [{"namespace": "a", "category": "x", "n": 1}, {"namespace": "b", "category": "x", "n": 2},
+           {"namespace": "a", "category": "y", "n": 3}, None]
+    ns_codes, lb_codes = {"a": 1, "b": 2}, {"x": 1, "y": 2}
+    c = compile_where({"namespace": "a"}, mds, ns_codes, "category", lb_codes)
+    assert (c.ns_code, c.label_code, c.mask_words, c.empty) == (1, 0xFFFFFFFF, None, False)
+    c = compile_where({"$and": [{"namespace": "b"}, {"category": {"$eq": "x"}}]}, mds, ns_codes, "category", lb_codes)
+    assert (c.ns_code, c.label_code, c.mask_words) == (2, 1, None)
+    c = compile_where({"$and": [{"namespace": "a"}, {"n": {"$gte": 2}}]}, mds, ns_codes, "category", lb_codes)
+    assert c.ns_code == 1 and c.mask_words.tolist() == [0b0110]
+    c = compile_where({"$or": [{"namespace": "a"}, {"n": 2}]}, mds, ns_codes, "category", lb_codes)
+    assert c.ns_code == 0xFFFFFFFF and c.mask_words.tolist() == [0b0111]
+    assert compile_where({"namespace": "zzz"}, mds, ns_codes, "category", lb_codes).empty
+    assert compile_where({"n": 99}, mds, ns_codes, "category", lb_codes).empty
+    alive = np.array([True, False, True, True])
+    c = compile_where(None, mds, ns_codes, "category", lb_codes, alive=alive)
+    assert c.mask_words.tolist() == [0b1101]
+    assert compile_where(None, mds, ns_codes, "category", lb_codes).mask_words is None
+    assert pack_mask(np.ones(33, bool)).tolist() == [0xFFFFFFFF, 1]
+    assert evaluate({"k": {"$nin": [1]}}, {}) and not evaluate({"k": 1}, None)
+    for bad in ({}, {"a": 1, "b": 2}, {"$and": [{"a": 1}]}, {"a": {"$regex": "x"}}, {"a": {"$in": 3}}, {"a": [1]}, "x"):
+        with pytest.raises(ValueError):
+            validate_where(bad)
+
+
+def test_default_embedder_is_deterministic_unit_and_nonnegative():
+    from codd_query_engine_b200.embedding import HashedBagOfWordsEmbedding
+
+    e = HashedBagOfWordsEmbedding()
+    a = e(["CPU utilization percentage", "cpu   UTILIZATION percentage!", "", "Memory in bytes"])
+    assert a.shape == (4, 384) and a.dtype == np.float32 and (a >= 0).all()
+    assert np.array_equal(a[0], a[1]) and np.allclose(np.linalg.norm(a[[0, 3]], axis=1), 1, atol=1e-6)
+    assert not a[2].any()
+    assert a[0] @ e(["cpu utilization"])[0] > a[3] @ e(["cpu utilization"])[0]
+    assert e([]).shape == (0, 384)

@@ -1,0 +1,156 @@
+"""The reference's own executable spec for the path, re-run against this package.
+
+Scenarios follow tests/unit/codd_dal/metrics/test_metrics_semantic_metadata_store.py:39-216 and
+tests/integration/codd_dal/metrics/test_metrics_semantic_metadata_store_integration.py:26-175 of the
+reference (8 live unit tests + 1 integration workflow).  They run twice: on the CPU with the
+oracle-backed test double substituted for native.NativeIndex (host logic), and -- marked gpu --
+through the real CUDA library.
+"""
+import pytest
+
+from codd_query_engine_b200 import client as client_mod
+from codd_query_engine_b200.semantic_store import MetricsSemanticMetadataStore
+from tests.doubles import OracleIndex
+
+
+@pytest.fixture(params=["double", pytest.param("native", marks=pytest.mark.gpu)])
+def chromadb_client(request, monkeypatch):
+    if request.param == "double":
+        monkeypatch.setattr(client_mod, "NativeIndex", OracleIndex)
+    c = client_mod.Client(endpoint=("test", request.node.name))
+    yield c
+    c.reset()
+
+
+@pytest.fixture
+def store(chromadb_client, request):
+    return MetricsSemanticMetadataStore(chromadb_client, collection_name=f"test_{request.node.name}")
+
+
+def test_index_metadata_basic(store):
+    md = {"metric_name": "cpu.usage", "type": "gauge", "description": "CPU utilization percentage",
+          "unit": "percent", "category": "system", "subcategory": "cpu"}
+    assert store.index_metadata("test", md) == "test#cpu.usage"
+
+
+def test_index_metadata_all_fields(store):
+    md = {"metric_name": "http.request.duration", "type": "histogram",
+          "description": "HTTP request duration in milliseconds", "unit": "ms", "category": "application",
+          "subcategory": "http", "category_description": "Application-level metrics",
+          "golden_signal_type": "latency", "golden_signal_description": "Measures request latency",
+          "meter_type": "histogram", "meter_type_description": "Distribution of values over time"}
+    assert store.index_metadata("test", md) == "test#http.request.duration"
+
+
+def test_index_metadata_missing_required_field(store):
+    with pytest.raises(KeyError) as exc:
+        store.index_metadata("test", {"type": "gauge", "description": "Some metric"})
+    assert "metric_name" in str(exc.value)
+
+
+def test_index_metadata_upsert(store):
+    ns, name = "test_namespace", "memory.usage"
+    store.index_metadata(ns, {"metric_name": name, "description": "Memory usage version 1", "category": "system"})
+    out = store.index_metadata(ns, {"metric_name": name, "description": "Memory usage version 2 updated",
+                                    "category": "infrastructure"})
+    assert out == f"{ns}#{name}"
+    hits = store.search_metadata("memory usage version 2", n_results=1)
+    assert len(hits) > 0 and hits[0]["metric_name"] == name and "version 2" in hits[0]["description"]
+    assert store.collection.count() == 1
+
+
+def test_search_metadata_basic(store):
+    store.index_metadata("test", {"metric_name": "cpu.usage", "description": "CPU utilization percentage", "category": "system"})
+    store.index_metadata("test", {"metric_name": "memory.usage", "description": "Memory utilization in bytes", "category": "system"})
+    hits = store.search_metadata("CPU utilization")
+    assert len(hits) > 0 and hits[0]["metric_name"] == "cpu.usage"
+    assert "similarity_score" in hits[0] and 0 <= hits[0]["similarity_score"] <= 1
+
+
+def test_search_metadata_no_results(store):
+    assert store.search_metadata("some query") == []
+
+
+def test_search_metadata_ranking(store):
+    store.index_metadata("test", {"metric_name": "http.latency", "description": "HTTP request latency in milliseconds",
+                                  "golden_signal_type": "latency"})
+    store.index_metadata("test", {"metric_name": "db.query.time", "description": "Database query execution time",
+                                  "category": "database"})
+    store.index_metadata("test", {"metric_name": "network.bandwidth", "description": "Network bandwidth usage",
+                                  "category": "network"})
+    hits = store.search_metadata("request latency")
+    assert len(hits) == 3 and hits[0]["metric_name"] == "http.latency"
+    for a, b in zip(hits, hits[1:]):
+        assert a["similarity_score"] >= b["similarity_score"]
+
+
+def test_search_metadata_returns_all_fields(store):
+    md = {"metric_name": "test.metric", "type": "gauge", "description": "Test description", "unit": "bytes",
+          "category": "test_category", "subcategory": "test_subcategory", "category_description": "Category desc",
+          "golden_signal_type": "throughput", "golden_signal_description": "Measures throughput",
+          "meter_type": "gauge", "meter_type_description": "Gauge meter"}
+    store.index_metadata("test", md)
+    hits = store.search_metadata("test metric")
+    assert len(hits) > 0
+    for key, val in md.items():
+        assert hits[0][key] == val
+    assert hits[0]["namespace"] == "test"
+
+
+def test_metric_exists(store):
+    assert store.metric_exists("ns", "m") is False
+    store.index_metadata("ns", {"metric_name": "m", "description": "d"})
+    assert store.metric_exists("ns", "m") is True
+    assert store.metric_exists("other", "m") is False
+
+
+def test_complete_metric_semantic_metadata_workflow(store):
+    ns = "test:order_service"
+    common = {"category": "application", "subcategory": "http", "category_description": "Application-level performance metrics"}
+    a = store.index_metadata(ns, {"metric_name": "http.request.duration.p99", "type": "histogram",
+                                  "description": "99th percentile HTTP request duration for all endpoints",
+                                  "unit": "milliseconds", **common, "golden_signal_type": "latency",
+                                  "golden_signal_description": "Time taken to service requests",
+                                  "meter_type": "histogram",
+                                  "meter_type_description": "Distribution of request durations over time"})
+    assert a == f"{ns}#http.request.duration.p99"
+    b = store.index_metadata(ns, {"metric_name": "http.errors.5xx.rate", "type": "counter",
+                                  "description": "Rate of 5xx server errors per second", "unit": "errors_per_second",
+                                  **common, "golden_signal_type": "errors",
+                                  "golden_signal_description": "Rate of failed requests", "meter_type": "counter",
+                                  "meter_type_description": "Monotonically increasing count of errors"})
+    assert b == f"{ns}#http.errors.5xx.rate"
+    c = store.index_metadata(ns, {"metric_name": "http.requests.total", "type": "counter",
+                                  "description": "Total number of HTTP requests received", "unit": "requests",
+                                  **common, "golden_signal_type": "traffic",
+                                  "golden_signal_description": "Volume of requests served", "meter_type": "counter",
+                                  "meter_type_description": "Cumulative count of requests"})
+    assert c == f"{ns}#http.requests.total"
+
+    hits = store.search_metadata("request latency and response time", n_results=5)
+    assert len(hits) >= 2
+    assert hits[0]["metric_name"] == "http.request.duration.p99" and hits[0]["golden_signal_type"] == "latency"
+    assert 0 <= hits[0]["similarity_score"] <= 1
+
+    ns2 = "test:payment_service"
+    store.index_metadata(ns2, {"metric_name": "db.query.execution.time", "type": "histogram",
+                               "description": "Database query execution time in milliseconds", "unit": "milliseconds",
+                               "category": "infrastructure", "subcategory": "database", "golden_signal_type": "latency",
+                               "meter_type": "histogram"})
+    store.index_metadata(ns2, {"metric_name": "db.connections.active", "type": "gauge",
+                               "description": "Number of active database connections", "unit": "connections",
+                               "category": "infrastructure", "subcategory": "database",
+                               "golden_signal_type": "saturation", "meter_type": "gauge"})
+    # search is NOT namespace-scoped (reference integration test :143-148)
+    db_hits = store.search_metadata("latency", n_results=5)
+    assert len(db_hits) >= 1 and "db.query.execution.time" in [h["metric_name"] for h in db_hits[:3]]
+
+    again = store.index_metadata(ns, {"metric_name": "http.request.duration.p99", "type": "histogram",
+                                      "description": "UPDATED: 99th percentile latency for HTTP requests with improved accuracy",
+                                      "unit": "milliseconds", "category": "application", "subcategory": "http",
+                                      "golden_signal_type": "latency", "meter_type": "histogram"})
+    assert again == a
+    upd = store.search_metadata("improved accuracy latency", n_results=1)
+    assert len(upd) > 0 and upd[0]["metric_name"] == "http.request.duration.p99"
+    assert "UPDATED" in upd[0]["description"] and "improved accuracy" in upd[0]["description"]
+    assert store.collection.count() == 5
