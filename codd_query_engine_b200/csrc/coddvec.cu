@@ -96,6 +96,9 @@ struct PinBuf {
     ~PinBuf() { if (p) cudaFreeHost(p); }
 };
 
+// AUTO path: batches up to this size take the fp32-exact K2 scan, larger ones the tensor-core K3.
+constexpr int kAutoScanMaxBatch = 2;
+
 // Per-query scratch.  A context is used by one query batch at a time; `busy` orders reuse on a
 // different stream without blocking the host.
 struct QueryCtx {
@@ -260,7 +263,7 @@ int plan_scan(cv_index* idx, QueryCtx* c, int qb, int k, bool pred, ScanLaunch* 
 
 // Enqueue one query batch on `stream`.  d_q: [B][D] fp32 device, d_out: [B][k] device keys.
 int enqueue_query(cv_index* idx, QueryCtx* c, cudaStream_t stream, const float* d_q, const cv_query_params* p,
-                  const uint32_t* d_mask, uint64_t* d_out) {
+                  const uint32_t* d_mask, uint64_t* d_out, float* dump = nullptr, int64_t dump_ld = 0) {
     const int B = p->n_queries, k = p->k;
     const int64_t n = idx->n_committed.load(std::memory_order_acquire);
     const bool pred = d_mask != nullptr || p->ns_code != CV_ANY || p->label_code != CV_ANY;
@@ -271,7 +274,7 @@ int enqueue_query(cv_index* idx, QueryCtx* c, cudaStream_t stream, const float* 
     const int nch = (idx->C + 15) / 16;
     int path = p->path;
     const int max_qb = scan_max_qb(nch);
-    if (path == CV_PATH_AUTO) path = (B <= max_qb || !mma_supported(idx->Dp)) ? CV_PATH_SCAN : CV_PATH_MMA;
+    if (path == CV_PATH_AUTO) path = (B <= std::min(max_qb, kAutoScanMaxBatch) || !mma_supported(idx->Dp)) ? CV_PATH_SCAN : CV_PATH_MMA;
     const bool timed = idx->profiling.load() != 0;
     if (timed) CV_CUDA(cudaEventRecord(c->t0, stream));
     int64_t passes_bytes = 0;
@@ -294,6 +297,8 @@ int enqueue_query(cv_index* idx, QueryCtx* c, cudaStream_t stream, const float* 
         m.B = B;
         m.k = k;
         m.out = d_out;
+        m.dump = dump;
+        m.dump_ld = dump_ld;
         m.counter = c->d_counter;
         m.sm_count = idx->sm_count;
         m.stream = stream;
@@ -651,6 +656,57 @@ int cv_query(cv_index* idx, const float* q, const cv_query_params* p, float* out
             out_counts[b] = cnt;
         }
     }
+    return CV_OK;
+}
+
+}  // extern "C"
+
+namespace cv {
+cudaError_t launch_merge_keys(const uint64_t* in, int G, int b_stride, int k_in, int k_out, uint64_t* out, int nq,
+                              cudaStream_t stream) {
+    k_merge_keys<<<nq, 256, 0, stream>>>(in, G, b_stride, k_in, k_out, out);
+    return cudaGetLastError();
+}
+}  // namespace cv
+
+extern "C" {
+
+int cv_debug_mma_scores(cv_index* idx, const float* q, int32_t B, float* out_scores) {
+    if (!idx || !q || !out_scores || B < 1) return fail(CV_ERR_INVALID, "bad argument");
+    DeviceGuard dg(idx->cfg.device);
+    if (!dg.ok) return fail(CV_ERR_CUDA, "cudaSetDevice(%d) failed", idx->cfg.device);
+    const int64_t n = idx->n_committed.load(std::memory_order_acquire);
+    if (n == 0) return CV_OK;
+    std::shared_lock<std::shared_mutex> rd(idx->overwrite_mu);
+    QueryCtx* c = nullptr;
+    int rc;
+    if ((rc = acquire_ctx(idx, &c))) return rc;
+    struct Releaser {
+        cv_index* i; QueryCtx* c;
+        ~Releaser() { release_ctx(i, c); }
+    } rel{idx, c};
+    cudaStream_t s = c->stream;
+    CV_CUDA(cudaStreamWaitEvent(s, c->busy, 0));
+    const int Bpad = (B + 127) / 128 * 128;
+    DevBuf<float> d_dump, d_q;
+    DevBuf<uint64_t> d_out;
+    if ((rc = d_dump.reserve(static_cast<size_t>(Bpad) * n)) || (rc = d_q.reserve(static_cast<size_t>(B) * idx->D)) ||
+        (rc = d_out.reserve(static_cast<size_t>(B) * 1)))
+        return rc;
+    CV_CUDA(cudaMemcpyAsync(d_q.p, q, sizeof(float) * B * idx->D, cudaMemcpyHostToDevice, s));
+    CV_CUDA(cudaMemsetAsync(d_dump.p, 0xFF, sizeof(float) * Bpad * n, s));
+    cv_query_params p{};
+    p.n_queries = B;
+    p.k = 1;
+    p.ns_code = CV_ANY;
+    p.label_code = CV_ANY;
+    p.mask = nullptr;
+    p.path = CV_PATH_MMA;
+    rc = enqueue_query(idx, c, s, d_q.p, &p, nullptr, d_out.p, d_dump.p, n);
+    if (rc) { (void)cudaStreamSynchronize(s); return rc; }
+    CV_CUDA(cudaMemcpyAsync(out_scores, d_dump.p, sizeof(float) * B * n, cudaMemcpyDeviceToHost, s));
+    CV_CUDA(cudaEventRecord(c->busy, s));
+    CV_CUDA(cudaStreamSynchronize(s));
     return CV_OK;
 }
 

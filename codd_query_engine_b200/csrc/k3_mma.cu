@@ -1,10 +1,487 @@
-// k3_mma.cu -- K3 `gemm_topk`.  Placeholder: the tcgen05 path is not built yet.
+// k3_mma.cu -- K3 `gemm_topk`: batched scoring on the 5th-gen tensor cores with a fused top-k epilogue.
+//
+// Replaces the batched form of Collection.query (call site
+// codd_dal/metrics/metrics_semantic_metadata_store.py:314-316; chromadb accepts query batches) with an
+// exact scan:  S[q][row] = (Qhat_bf16[q] . E_bf16[row]) * scale[row], fp32 accumulate in TMEM.
+//
+// Shape of the work.  The query tile is the UMMA *M* operand (128 queries = 128 TMEM lanes, resident
+// in shared memory for the whole kernel), a tile of 128 corpus rows is the *N* operand (streamed once
+// from HBM by TMA, K-major, SWIZZLE_128B, 64-element K blocks through a 6-deep mbarrier ring), D is
+// the short K dimension (Dp/16 tcgen05.mma per tile).  With queries on the lanes every epilogue
+// thread owns ONE query: it keeps that query's running threshold in a register and its k-list
+// privately, so the fused top-k needs no atomics, no shuffles and no shared memory -- one FMUL +
+// one FSETP per score, and the B x N score matrix never leaves TMEM/registers.  The per-row scale
+// and the namespace / label / bitmask predicate are folded into one shared-memory vector per tile
+// (NaN = not eligible, so an ineligible score fails every comparison).
+//
+// Warp roles (192 threads, one CTA per SM, persistent): warp 0 = TMA producer (one elected lane),
+// warp 1 = TMEM allocator + MMA issuer (one elected lane), warps 2..5 = epilogue (TMEM lane quarter
+// = warp_id % 4).  Two TMEM accumulator stages (2 x 128 columns) overlap the MMAs of tile t+1 with the
+// epilogue of tile t.
+//
+// Roofline: algorithmic bytes = rows * (2*Dp + 4) per query tile pass, flops =
+// 2 * B * rows * Dp.  HBM-bound for B <~ 200, tensor-bound above.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/coddvec.h"
+#include "common.cuh"
 #include "k3_mma.cuh"
+#include "vmm.hpp"
+
 namespace cv {
-bool mma_supported(int) { return false; }
-std::string& mma_error() { static thread_local std::string e; return e; }
-int mma_enqueue(const MmaArgs&, MmaScratch&, std::atomic<int64_t>*) {
-    mma_error() = "tensor-core path not built";
-    return -5;
+
+namespace {
+
+constexpr int kQ = 128;          // queries per tile  (UMMA M, TMEM lanes)
+constexpr int kTN = 128;         // corpus rows per tile (UMMA N, TMEM columns per accumulator stage)
+constexpr int kKB = 64;          // K elements per shared-memory block = 128 bytes = one swizzle row
+constexpr int kBlockBytes = kTN * kKB * 2;  // 16 KiB: one [128 rows][64] bf16 block (Q or corpus)
+constexpr int kStages = 6;       // corpus ring depth (96 KiB in flight per SM)
+constexpr int kAccStages = 2;
+constexpr int kThreads = 192;
+constexpr int kMaxKBlocks = 8;   // Dp <= 512 keeps the query tile resident next to the ring
+constexpr uint32_t kTmemCols = kAccStages * kTN;  // 256
+
+constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
+constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
+constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
+
+struct KArgs {
+    const float* scale;
+    const uint32_t* ns;
+    const uint32_t* label;
+    const uint32_t* mask;
+    uint32_t ns_code, label_code;
+    int64_t n;
+    int kblocks;
+    int k;
+    uint32_t row_offset;
+    int n_tiles;
+    int q_tiles;
+    int P;          // CTAs sharing one query tile
+    int Bpad;
+    uint64_t* lists;  // [P][Bpad][k]
+    float* dump;      // debug: [Bpad][dump_ld] scores, or nullptr
+    int64_t dump_ld;
+    uint64_t corpus_hint;
+};
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "CV_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra CV_DONE;\n\t"
+        "bra CV_WAIT;\n\t"
+        "CV_DONE:\n\t"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, uint64_t hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "l"(hint)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, bf16 x bf16 -> fp32, issued by one thread for the CTA
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier when every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major operand, SWIZZLE_128B, rows at a 128-byte pitch:
+//   bits [0,14) start address >> 4, [16,30) leading byte offset >> 4 (unused for swizzled K-major: 1),
+//   [32,46) stride byte offset >> 4 (8 rows * 128 B = 1024 B between 8-row core-matrix groups),
+//   [46,48) descriptor version = 1 (sm_100), [61,64) layout type = 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+// Instruction descriptor for kind::f16: fp32 accumulate (bits 4-5 = 1), A = B = bf16 (bits 7-9, 10-12 = 1),
+// both K-major (bits 15, 16 = 0), N >> 3 at bits 17-22, M >> 4 at bits 24-28.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// per-thread sorted insertion into a private k-list (global memory, L1/L2 resident; rare)
+__device__ __noinline__ int list_insert_private(uint64_t* list, int k, int cnt, uint64_t key) {
+    int j = cnt < k ? cnt : k - 1;
+    while (j > 0 && list[j - 1] < key) {
+        list[j] = list[j - 1];
+        --j;
+    }
+    list[j] = key;
+    return cnt < k ? cnt + 1 : cnt;
+}
+
+// ------------------------------------------------------------------------------------------ query prep
+// Normalise fp32 queries exactly like the oracle (fp64 norm, fp32 divide), round to bf16, zero-pad to
+// [Bpad][Dp].  One warp per query row.
+__global__ void __launch_bounds__(128) k_prep_queries(const float* q, int B, int Bpad, int D, int Dp, int cosine,
+                                                      __nv_bfloat16* out) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (row >= Bpad) return;
+    __nv_bfloat16* o = out + static_cast<size_t>(row) * Dp;
+    if (row >= B) {
+        for (int d = lane; d < Dp; d += 32) o[d] = __float2bfloat16_rn(0.0f);
+        return;
+    }
+    const float* r = q + static_cast<size_t>(row) * D;
+    float safe = 1.0f;
+    if (cosine) {
+        double ss = 0.0;
+        for (int d = lane; d < D; d += 32) {
+            double v = static_cast<double>(r[d]);
+            ss += v * v;
+        }
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) ss += __shfl_xor_sync(kFullMask, ss, o2);
+        float nrm = static_cast<float>(sqrt(ss));
+        safe = nrm > 0.0f ? nrm : 1.0f;
+    }
+    for (int d = lane; d < Dp; d += 32) o[d] = __float2bfloat16_rn(d < D ? __fdiv_rn(r[d], safe) : 0.0f);
+}
+
+// ------------------------------------------------------------------------------------------ main kernel
+template <bool DUMP>
+__global__ void __launch_bounds__(kThreads, 1)
+k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_e, const KArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    // carve-up (all block bases 1024-byte aligned, as SWIZZLE_128B requires)
+    unsigned char* sm_q = smem;                                           // kblocks x 16 KiB
+    unsigned char* sm_ring = smem + static_cast<size_t>(a.kblocks) * kBlockBytes;  // kStages x 16 KiB
+    float* sm_scale = reinterpret_cast<float*>(sm_ring + static_cast<size_t>(kStages) * kBlockBytes);  // [2][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm_scale + kAccStages * kTN);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1 + 2 * kAccStages);
+
+    const uint32_t bar_full = smem_u32(bars);                  // [kStages]
+    const uint32_t bar_empty = bar_full + 8 * kStages;         // [kStages]
+    const uint32_t bar_q = bar_empty + 8 * kStages;            // [1]
+    const uint32_t bar_tfull = bar_q + 8;                      // [kAccStages]
+    const uint32_t bar_tempty = bar_tfull + 8 * kAccStages;    // [kAccStages]
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int qt = blockIdx.x % a.q_tiles;
+    const int p = blockIdx.x / a.q_tiles;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        mbar_init(bar_q, 1);
+        for (int s = 0; s < kAccStages; ++s) {
+            mbar_init(bar_tfull + 8 * s, 1);
+            mbar_init(bar_tempty + 8 * s, 4);  // one arrival per epilogue warp
+        }
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================================================================== TMA producer
+        if (lane == 0) {
+            tma_prefetch_desc(&tmap_q);
+            tma_prefetch_desc(&tmap_e);
+            mbar_arrive_expect_tx(bar_q, static_cast<uint32_t>(a.kblocks) * kBlockBytes);
+            for (int kb = 0; kb < a.kblocks; ++kb)
+                tma_load_2d(smem_u32(sm_q + static_cast<size_t>(kb) * kBlockBytes), &tmap_q, bar_q, kb * kKB, qt * kQ, kEvictLast);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = p; t < a.n_tiles; t += a.P) {
+                for (int kb = 0; kb < a.kblocks; ++kb) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    mbar_arrive_expect_tx(bar_full + 8 * stage, kBlockBytes);
+                    tma_load_2d(smem_u32(sm_ring + static_cast<size_t>(stage) * kBlockBytes), &tmap_e, bar_full + 8 * stage,
+                                kb * kKB, t * kTN, a.corpus_hint);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(kQ, kTN);
+            mbar_wait(bar_q, 0);
+            tc_fence_after();
+            int stage = 0, as = 0;
+            uint32_t phase = 0, aphase = 0;
+            for (int t = p; t < a.n_tiles; t += a.P) {
+                mbar_wait(bar_tempty + 8 * as, aphase ^ 1);  // epilogue has drained this accumulator stage
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * kTN);
+                for (int kb = 0; kb < a.kblocks; ++kb) {
+                    mbar_wait(bar_full + 8 * stage, phase);  // TMA bytes have landed
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(sm_q + static_cast<size_t>(kb) * kBlockBytes);
+                    const uint32_t b_addr = smem_u32(sm_ring + static_cast<size_t>(stage) * kBlockBytes);
+#pragma unroll
+                    for (int ks = 0; ks < kKB / 16; ++ks)  // UMMA_K = 16 bf16 = 32 bytes inside the swizzle row
+                        umma_bf16(tmem_d, umma_desc_sw128(a_addr + ks * 32), umma_desc_sw128(b_addr + ks * 32), idesc,
+                                  (kb | ks) != 0 ? 1u : 0u);
+                    umma_commit(bar_empty + 8 * stage);  // frees the ring slot once these MMAs have read it
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(bar_tfull + 8 * as);  // accumulator complete -> epilogue
+                if (++as == kAccStages) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else {
+        // ===================================================================== epilogue (128 threads)
+        const int et = threadIdx.x - 64;                 // 0..127: column this thread stages scale for
+        const int qlane = 32 * (warp & 3) + lane;        // TMEM lane = query within the tile
+        const int qglobal = qt * kQ + qlane;
+        uint64_t* list = a.lists + (static_cast<size_t>(p) * a.Bpad + qglobal) * a.k;
+        for (int j = 0; j < a.k; ++j) list[j] = 0ull;
+        int cnt = 0;
+        float thr = -INFINITY;
+        const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(32 * (warp & 3)) << 16);
+        const bool pred = a.mask != nullptr || a.ns_code != kAny || a.label_code != kAny;
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int t = p; t < a.n_tiles; t += a.P) {
+            // stage scale * eligibility for this tile's 128 rows (NaN = skip)
+            {
+                const int64_t row = static_cast<int64_t>(t) * kTN + et;
+                float sc = __int_as_float(0x7FC00000);
+                if (row < a.n) {
+                    bool ok = true;
+                    if (pred) {
+                        if (a.ns_code != kAny) ok = __ldg(a.ns + row) == a.ns_code;
+                        if (ok && a.label_code != kAny) ok = __ldg(a.label + row) == a.label_code;
+                        if (ok && a.mask) ok = (__ldg(a.mask + (row >> 5)) >> (row & 31)) & 1u;
+                    }
+                    if (ok) sc = __ldg(a.scale + row);
+                }
+                sm_scale[as * kTN + et] = sc;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
+            mbar_wait(bar_tfull + 8 * as, aphase);
+            tc_fence_after();
+            const float* sc_tile = sm_scale + as * kTN;
+            const uint32_t row0 = a.row_offset + static_cast<uint32_t>(t) * kTN;
+#pragma unroll 1
+            for (int c = 0; c < kTN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld32(lane_base + static_cast<uint32_t>(as * kTN + c * 32), v);
+                tmem_ld_wait();
+                bool any = false;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float s = __uint_as_float(v[j]) * sc_tile[c * 32 + j];
+                    v[j] = __float_as_uint(s);
+                    any |= s > thr;
+                }
+                if (DUMP) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int64_t row = static_cast<int64_t>(t) * kTN + c * 32 + j;
+                        if (row < a.n) a.dump[static_cast<size_t>(qglobal) * a.dump_ld + row] = __uint_as_float(v[j]);
+                    }
+                }
+                if (any) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float s = __uint_as_float(v[j]);
+                        if (s > thr) {
+                            cnt = list_insert_private(list, a.k, cnt, pack_key(s, row0 + c * 32 + j));
+                            thr = cnt == a.k ? key_score(list[a.k - 1]) : -INFINITY;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+            if (++as == kAccStages) { as = 0; aphase ^= 1; }
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+size_t mma_smem_bytes(int kblocks) {
+    return static_cast<size_t>(kblocks + kStages) * kBlockBytes + kAccStages * kTN * sizeof(float) +
+           (2 * kStages + 1 + 2 * kAccStages) * sizeof(uint64_t) + 16;
+}
+
+thread_local std::string g_mma_err;
+
+int mma_fail(int code, const std::string& msg) {
+    g_mma_err = msg;
+    return code;
+}
+
+int encode_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint32_t box_outer) {
+    const DriverApi& d = driver_api();
+    if (!d.ok) return mma_fail(CV_ERR_CUDA, d.why);
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {inner * 2};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(kKB), box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = d.tensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+                                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return mma_fail(CV_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string(r));
+    return 0;
+}
+
+}  // namespace
+
+bool mma_supported(int Dp) { return Dp % kKB == 0 && Dp / kKB <= kMaxKBlocks; }
+std::string& mma_error() { return g_mma_err; }
+
+#define MMA_CUDA(call)                                                                                  \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess) {                                                                       \
+            (void)cudaGetLastError();                                                                   \
+            return mma_fail(e__ == cudaErrorMemoryAllocation ? CV_ERR_OOM : CV_ERR_CUDA,                \
+                            std::string(#call) + " failed: " + cudaGetErrorString(e__));                \
+        }                                                                                               \
+    } while (0)
+
+int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* launches) {
+    if (!mma_supported(m.Dp))
+        return mma_fail(CV_ERR_UNSUPPORTED, "tensor-core path supports padded dim <= 512 (got " + std::to_string(m.Dp) + ")");
+    const int kblocks = m.Dp / kKB;
+    const int n_tiles = static_cast<int>((m.n + kTN - 1) / kTN);
+    const size_t smem = mma_smem_bytes(kblocks);
+    auto kernel = m.dump ? k_mma_topk<true> : k_mma_topk<false>;
+    MMA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    // batches larger than one wave of query tiles are processed in slices
+    const int max_qt = m.sm_count;
+    int done = 0;
+    while (done < m.B) {
+        const int Bs = std::min(m.B - done, max_qt * kQ);
+        const int QT = (Bs + kQ - 1) / kQ;
+        const int Bpad = QT * kQ;
+        int P = m.sm_count / QT;
+        if (P > n_tiles) P = n_tiles;
+        if (P < 1) P = 1;
+        // scratch: [Qb bf16 Bpad x Dp][lists P x Bpad x k u64][dump]
+        const size_t q_bytes = (static_cast<size_t>(Bpad) * m.Dp * 2 + 1023) / 1024 * 1024;
+        const size_t list_bytes = static_cast<size_t>(P) * Bpad * m.k * sizeof(uint64_t);
+        const size_t need = q_bytes + list_bytes;
+        if (need > scratch.cap) {
+            if (scratch.p) {
+                MMA_CUDA(cudaStreamSynchronize(m.stream));
+                cudaFree(scratch.p);
+                scratch.p = nullptr;
+                scratch.cap = 0;
+            }
+            MMA_CUDA(cudaMalloc(&scratch.p, need + need / 2));
+            scratch.cap = need + need / 2;
+        }
+        __nv_bfloat16* qb = reinterpret_cast<__nv_bfloat16*>(scratch.p);
+        uint64_t* lists = reinterpret_cast<uint64_t*>(scratch.p + q_bytes);
+
+        k_prep_queries<<<(Bpad + 3) / 4, 128, 0, m.stream>>>(m.q + static_cast<size_t>(done) * m.D, Bs, Bpad, m.D, m.Dp,
+                                                             m.cosine ? 1 : 0, qb);
+        MMA_CUDA(cudaGetLastError());
+
+        CUtensorMap tq, te;
+        int rc;
+        if ((rc = encode_map(&tq, qb, m.Dp, Bpad, kQ))) return rc;
+        if ((rc = encode_map(&te, m.E, m.Dp, static_cast<uint64_t>(m.n), kTN))) return rc;
+
+        KArgs a;
+        a.scale = m.scale;
+        a.ns = m.ns;
+        a.label = m.label;
+        a.mask = m.mask;
+        a.ns_code = m.ns_code;
+        a.label_code = m.label_code;
+        a.n = m.n;
+        a.kblocks = kblocks;
+        a.k = m.k;
+        a.row_offset = m.row_offset;
+        a.n_tiles = n_tiles;
+        a.q_tiles = QT;
+        a.P = P;
+        a.Bpad = Bpad;
+        a.lists = lists;
+        a.dump = m.dump ? m.dump + static_cast<size_t>(done) * m.dump_ld : nullptr;
+        a.dump_ld = m.dump_ld;
+        a.corpus_hint = QT > 1 ? kEvictNormal : kEvictFirst;
+        kernel<<<QT * P, kThreads, smem, m.stream>>>(tq, te, a);
+        MMA_CUDA(cudaGetLastError());
+        MMA_CUDA(launch_merge_keys(lists, P, Bpad, m.k, m.k, m.out + static_cast<size_t>(done) * m.k, Bs, m.stream));
+        if (launches) launches->fetch_add(3);
+        done += Bs;
+        if (done < m.B) MMA_CUDA(cudaStreamSynchronize(m.stream));  // scratch is reused by the next slice
+    }
+    return 0;
+}
+
 }  // namespace cv

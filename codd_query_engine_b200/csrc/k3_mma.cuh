@@ -26,6 +26,8 @@ struct MmaArgs {
     const float* q;         // [B][D] fp32 raw (device)
     int B, k;
     uint64_t* out;          // [B][k]
+    float* dump;            // debug: write every score to dump[b * dump_ld + row] (device), or nullptr
+    int64_t dump_ld;
     unsigned int* counter;
     int sm_count;
     cudaStream_t stream;
@@ -35,5 +37,9 @@ bool mma_supported(int Dp);
 // returns 0 or a CV_ERR_* code; text in mma_error().  *launches is incremented per kernel launch.
 int mma_enqueue(const MmaArgs& a, MmaScratch& scratch, std::atomic<int64_t>* launches);
 std::string& mma_error();
+
+// K4 launcher (kernel lives in coddvec.cu): merge G lists [G][b_stride][k_in] -> out[nq][k_out]
+cudaError_t launch_merge_keys(const uint64_t* in, int G, int b_stride, int k_in, int k_out, uint64_t* out, int nq,
+                              cudaStream_t stream);
 
 }  // namespace cv

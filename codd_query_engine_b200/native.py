@@ -116,6 +116,7 @@ def load_library() -> ctypes.CDLL:
         "cv_decode_keys": (None, [vp, i64, vp, vp]),
         "cv_encode_key": (u64, [ctypes.c_float, u32]),
         "cv_get_rows": (ctypes.c_int, [vp, vp, i64, vp, vp, vp, vp]),
+        "cv_debug_mma_scores": (ctypes.c_int, [vp, vp, i32, vp]),
         "cv_count": (i64, [vp]),
         "cv_dim": (i32, [vp]),
         "cv_set_profiling": (ctypes.c_int, [vp, i32]),
@@ -134,7 +135,7 @@ def load_library() -> ctypes.CDLL:
 
 EXPORTED_SYMBOLS = (
     "cv_create", "cv_destroy", "cv_upsert", "cv_upsert_device", "cv_query", "cv_query_device",
-    "cv_merge_keys_device", "cv_decode_keys", "cv_encode_key", "cv_get_rows", "cv_count", "cv_dim",
+    "cv_merge_keys_device", "cv_decode_keys", "cv_encode_key", "cv_get_rows", "cv_debug_mma_scores", "cv_count", "cv_dim",
     "cv_set_profiling", "cv_stats", "cv_synchronize", "cv_last_error", "cv_version",
 )
 
@@ -283,6 +284,13 @@ class NativeIndex:
         lb = np.empty(n, dtype=np.uint32)
         _check(self._lib.cv_get_rows(self._h, _ptr(r), n, _ptr(vec), _ptr(scale), _ptr(ns), _ptr(lb)))
         return vec, scale, ns, lb
+
+    def debug_mma_scores(self, queries: np.ndarray) -> np.ndarray:
+        """Every score the tensor-core path computes: [B][count] fp32 (testing aid)."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        out = np.empty((q.shape[0], len(self)), dtype=np.float32)
+        _check(self._lib.cv_debug_mma_scores(self._h, _ptr(q), q.shape[0], _ptr(out)))
+        return out
 
     def set_profiling(self, enabled: bool) -> None:
         _check(self._lib.cv_set_profiling(self._h, 1 if enabled else 0))

@@ -133,6 +133,10 @@ uint64_t cv_encode_key(float score, uint32_t global_row);
 int cv_get_rows(cv_index* idx, const int64_t* rows, int64_t n, uint16_t* out_bf16, float* out_scale,
                 uint32_t* out_ns, uint32_t* out_label);
 
+/* Testing aid: run the tensor-core path (K3) for B queries and return EVERY score it computed,
+ * out_scores[B][count] (host), so that tests can compare the whole score matrix with the oracle. */
+int cv_debug_mma_scores(cv_index* idx, const float* q, int32_t B, float* out_scores);
+
 int64_t cv_count(const cv_index* idx);
 int32_t cv_dim(const cv_index* idx);
 int cv_set_profiling(cv_index* idx, int32_t enabled);

@@ -1,0 +1,164 @@
+"""GPU parity tests of the tensor-core path (K3: TMA + tcgen05 + fused top-k) against the oracle."""
+import numpy as np
+import pytest
+
+from oracle import brute_force as bf
+from tests.parity import check_topk, oracle_full_scores
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3  # BASELINE.json north_star: scores within 1e-3 absolute (queries are rounded to bf16 on this path)
+
+
+@pytest.fixture(scope="module")
+def native(native_lib):
+    from codd_query_engine_b200 import native as nat
+
+    return nat
+
+
+def build(native, n, D, seed, metric=bf.METRIC_COSINE, **kw):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((n, D)).astype(np.float32)
+    idx = native.NativeIndex(D, metric=metric, row_offset=kw.pop("row_offset", 0))
+    idx.upsert(x, **kw)
+    vec, scale, _, _ = idx.get_rows(np.arange(n))
+    return idx, vec, scale, rng
+
+
+def bf16_query_scores(stored, scale, q, metric=bf.METRIC_COSINE):
+    """What K3 computes exactly: the normalised query rounded to bf16, fp32 accumulate."""
+    qhat = bf.normalise_query(q, metric)
+    qb = bf.bf16_bits_to_f32(bf.f32_to_bf16_bits(qhat))
+    return bf.scores_fp32(stored, scale, qb)
+
+
+@pytest.mark.parametrize("D,B,n", [(384, 3, 1000), (384, 128, 4096), (64, 1, 130), (128, 130, 777), (512, 17, 2049),
+                                   (100, 5, 500), (384, 260, 3000)])
+def test_full_score_matrix(native, D, B, n):
+    """Every score the tcgen05 pipeline produces (all tiles, all K blocks, tails) vs the oracle."""
+    idx, stored, scale, rng = build(native, n, D, seed=D + B + n)
+    q = rng.standard_normal((B, D)).astype(np.float32)
+    got = idx.debug_mma_scores(q)
+    want = bf16_query_scores(stored, scale, q)
+    assert got.shape == want.shape
+    assert np.isfinite(got).all()
+    assert np.abs(got - want).max() <= 3e-6, f"max err {np.abs(got - want).max()}"
+    assert np.abs(got - oracle_full_scores(stored, scale, q)).max() <= TOL
+    idx.close()
+
+
+@pytest.mark.parametrize("D,B,k,n", [(384, 1, 10, 70001), (384, 16, 10, 70001), (384, 128, 10, 50000),
+                                     (384, 129, 10, 50000), (384, 300, 5, 30000), (384, 64, 100, 20000),
+                                     (384, 8, 128, 5000), (384, 5, 10, 7), (384, 5, 10, 128), (384, 5, 10, 129),
+                                     (64, 32, 1, 10000), (512, 40, 20, 10000), (200, 9, 10, 10000)])
+def test_mma_topk_parity(native, D, B, k, n):
+    idx, stored, scale, rng = build(native, n, D, seed=D * 7 + B * 3 + k + n)
+    q = rng.standard_normal((B, D)).astype(np.float32)
+    scores, rows, counts = idx.query(q, k, path=native.PATH_MMA)
+    assert idx.stats().last_path == native.PATH_MMA
+    # exactness against what the tensor path computes ...
+    check_topk(scores, rows, counts, bf16_query_scores(stored, scale, q), None, k, tol=3e-6)
+    # ... and the acceptance bar against the fp32 oracle
+    check_topk(scores, rows, counts, oracle_full_scores(stored, scale, q), None, k, tol=TOL)
+    idx.close()
+
+
+def test_mma_and_scan_paths_agree(native):
+    idx, stored, scale, rng = build(native, 40000, 384, seed=5)
+    q = rng.standard_normal((4, 384)).astype(np.float32)
+    s1, r1, c1 = idx.query(q, 10, path=native.PATH_SCAN)
+    s2, r2, c2 = idx.query(q, 10, path=native.PATH_MMA)
+    assert np.array_equal(c1, c2) and np.abs(s1 - s2).max() <= TOL
+    same = (r1 == r2).mean()
+    assert same > 0.9  # random data: near-ties within 1e-3 are rare
+    idx.close()
+
+
+def test_mma_ties_and_duplicates(native):
+    rng = np.random.default_rng(7)
+    D, k = 384, 10
+    base = rng.standard_normal((50, D)).astype(np.float32)
+    x = np.concatenate([base] * 40)
+    idx = native.NativeIndex(D)
+    idx.upsert(x)
+    q = np.repeat(base[3:4], 6, axis=0) + 0.0
+    scores, rows, counts = idx.query(q, k, path=native.PATH_MMA)
+    for b in range(6):
+        assert rows[b].tolist() == [3 + 50 * i for i in range(k)]  # exact ties -> ascending row id
+        assert len(set(scores[b].tolist())) == 1
+    idx.close()
+
+
+def test_mma_predicates_and_row_offset(native):
+    rng = np.random.default_rng(11)
+    n, D, k, B = 30000, 384, 20, 7
+    ns = rng.integers(0, 10, n).astype(np.uint32)
+    label = rng.integers(0, 3, n).astype(np.uint32)
+    idx, stored, scale, rng = build(native, n, D, seed=12, ns_codes=ns, label_codes=label, row_offset=5000)
+    q = rng.standard_normal((B, D)).astype(np.float32)
+    full = bf16_query_scores(stored, scale, q)
+    bits = rng.random(n) < 0.05
+    words = np.packbits(np.concatenate([bits, np.zeros((-n) % 32, bool)]), bitorder="little").view(np.uint32)
+    for kw, el in (({"ns_code": 3}, ns == 3), ({"ns_code": 3, "label_code": 1}, (ns == 3) & (label == 1)),
+                   ({"mask": words}, bits), ({"mask": words, "ns_code": 5}, bits & (ns == 5))):
+        s, r, c = idx.query(q, k, path=native.PATH_MMA, **kw)
+        check_topk(s, r, c, full, el, k, tol=3e-6, row_offset=5000)
+    s, r, c = idx.query(q, k, ns_code=77, path=native.PATH_MMA)
+    assert (c == 0).all() and (r == -1).all()
+    idx.close()
+
+
+def test_mma_ip_metric(native):
+    idx, stored, scale, rng = build(native, 20000, 384, seed=13, metric=bf.METRIC_IP)
+    q = rng.standard_normal((9, 384)).astype(np.float32)
+    s, r, c = idx.query(q, 10, path=native.PATH_MMA)
+    check_topk(s, r, c, bf16_query_scores(stored, scale, q, bf.METRIC_IP), None, 10, tol=5e-5)
+    idx.close()
+
+
+def test_mma_unsupported_dim_is_loud_and_auto_falls_to_scan(native):
+    idx, stored, scale, rng = build(native, 2000, 768, seed=14)
+    q = rng.standard_normal((8, 768)).astype(np.float32)
+    with pytest.raises(native.NativeError):
+        idx.query(q, 5, path=native.PATH_MMA)
+    s, r, c = idx.query(q, 5)  # AUTO
+    assert idx.stats().last_path == native.PATH_SCAN
+    check_topk(s, r, c, oracle_full_scores(stored, scale, q), None, 5, tol=2e-6)
+    idx.close()
+
+
+def test_auto_path_selection(native):
+    idx, stored, scale, rng = build(native, 5000, 384, seed=15)
+    idx.query(rng.standard_normal((1, 384)).astype(np.float32), 5)
+    assert idx.stats().last_path == native.PATH_SCAN
+    idx.query(rng.standard_normal((32, 384)).astype(np.float32), 5)
+    assert idx.stats().last_path == native.PATH_MMA
+    idx.close()
+
+
+def test_large_batch_and_large_corpus_properties(native):
+    """BASELINE-sized shapes through size-independent properties: planted neighbours are found."""
+    import torch
+
+    n, D, B, k = 2_000_000, 384, 1024, 10
+    idx = native.NativeIndex(D, capacity_rows=n)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for lo in range(0, n, 500_000):
+        x = torch.randn((500_000, D), device="cuda", generator=g)
+        idx.upsert_device(x.data_ptr(), 500_000)
+    del x
+    rng = np.random.default_rng(21)
+    planted = rng.choice(n, B, replace=False)
+    vec, scale, _, _ = idx.get_rows(np.sort(planted))
+    order = np.argsort(np.argsort(planted))
+    q = bf.bf16_bits_to_f32(vec)[order]  # query b == stored row planted[b]
+    s, r, c = idx.query(q, k, path=native.PATH_MMA)
+    assert (c == k).all()
+    assert np.array_equal(r[:, 0], planted)           # each query's own row is its top hit ...
+    assert np.abs(s[:, 0] - 1.0).max() < 2e-3          # ... with cosine ~ 1
+    assert (np.diff(s, axis=1) <= 0).all()             # descending
+    assert (s[:, 1] < 0.5).all()                       # random 384-d vectors are nearly orthogonal
+    s1, r1, c1 = idx.query(q[:4], k, path=native.PATH_SCAN)
+    assert np.array_equal(r1[:, 0], planted[:4]) and np.abs(s1 - s[:4]).max() <= TOL
+    idx.close()
