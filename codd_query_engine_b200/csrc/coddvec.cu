@@ -97,7 +97,7 @@ struct PinBuf {
 };
 
 // AUTO path: batches up to this size take the fp32-exact K2 scan, larger ones the tensor-core K3.
-constexpr int kAutoScanMaxBatch = 2;
+constexpr int kAutoScanMaxBatch = 1;
 
 // Per-query scratch.  A context is used by one query batch at a time; `busy` orders reuse on a
 // different stream without blocking the host.

@@ -62,7 +62,9 @@ struct KArgs {
     int q_tiles;
     int P;          // CTAs sharing one query tile
     int Bpad;
+    int B;            // real queries in this slice (lanes >= B are padding)
     uint64_t* lists;  // [P][Bpad][k]
+    uint32_t* gthr;   // [Bpad] shared per-query lower bounds on the k-th best score (ordered-float encoding)
     float* dump;      // debug: [Bpad][dump_ld] scores, or nullptr
     int64_t dump_ld;
     uint64_t corpus_hint;
@@ -163,25 +165,53 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
-// per-thread sorted insertion into a private k-list (global memory, L1/L2 resident; rare)
-__device__ __noinline__ int list_insert_private(uint64_t* list, int k, int cnt, uint64_t key) {
-    int j = cnt < k ? cnt : k - 1;
-    while (j > 0 && list[j - 1] < key) {
-        list[j] = list[j - 1];
-        --j;
+// order-preserving float <-> uint32 (same mapping as the high word of a result key); 0 = "nothing yet"
+__device__ __forceinline__ uint32_t ord_of(float f) {
+    uint32_t u = __float_as_uint(f + 0.0f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord_to_float(uint32_t o) {
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o);
+}
+// lower bound published by other CTAs -> strict threshold: s > result  <=>  s >= published score
+__device__ __forceinline__ float shared_threshold(uint32_t g) { return g <= 1u ? -INFINITY : ord_to_float(g - 1u); }
+
+// register-resident descending list: branch-free bubble insertion, no memory traffic
+template <int KREG>
+__device__ __forceinline__ void list_insert_regs(uint64_t (&L)[KREG], uint64_t key) {
+    uint64_t cur = key;
+#pragma unroll
+    for (int j = 0; j < KREG; ++j) {
+        const bool gt = cur > L[j];
+        const uint64_t hi = gt ? cur : L[j];
+        cur = gt ? L[j] : cur;
+        L[j] = hi;
     }
-    list[j] = key;
-    return cnt < k ? cnt + 1 : cnt;
+}
+
+// v[j] for a runtime j without spilling v to local memory: a 31-select binary tree
+__device__ __forceinline__ uint32_t pick32(const uint32_t (&v)[32], int j) {
+    uint32_t a[16], b[8], c[4], d[2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = (j & 1) ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) b[i] = (j & 2) ? a[2 * i + 1] : a[2 * i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[i] = (j & 4) ? b[2 * i + 1] : b[2 * i];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) d[i] = (j & 8) ? c[2 * i + 1] : c[2 * i];
+    return (j & 16) ? d[1] : d[0];
 }
 
 // ------------------------------------------------------------------------------------------ query prep
 // Normalise fp32 queries exactly like the oracle (fp64 norm, fp32 divide), round to bf16, zero-pad to
 // [Bpad][Dp].  One warp per query row.
 __global__ void __launch_bounds__(128) k_prep_queries(const float* q, int B, int Bpad, int D, int Dp, int cosine,
-                                                      __nv_bfloat16* out) {
+                                                      __nv_bfloat16* out, uint32_t* gthr) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (row >= Bpad) return;
+    if (lane == 0) gthr[row] = 0u;
     __nv_bfloat16* o = out + static_cast<size_t>(row) * Dp;
     if (row >= B) {
         for (int d = lane; d < Dp; d += 32) o[d] = __float2bfloat16_rn(0.0f);
@@ -204,7 +234,7 @@ __global__ void __launch_bounds__(128) k_prep_queries(const float* q, int B, int
 }
 
 // ------------------------------------------------------------------------------------------ main kernel
-template <bool DUMP>
+template <bool DUMP, int KREG>
 __global__ void __launch_bounds__(kThreads, 1)
 k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_e, const KArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -299,9 +329,21 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
         const int qlane = 32 * (warp & 3) + lane;        // TMEM lane = query within the tile
         const int qglobal = qt * kQ + qlane;
         uint64_t* list = a.lists + (static_cast<size_t>(p) * a.Bpad + qglobal) * a.k;
-        for (int j = 0; j < a.k; ++j) list[j] = 0ull;
-        int cnt = 0;
-        float thr = -INFINITY;
+        constexpr int KR = KREG > 0 ? KREG : 1;
+        // k <= KREG: the list lives in registers, right-aligned -- slots [KREG-k, KREG) hold the top-k
+        // descending, the slots before them are never-beaten sentinels -- so the k-th best is always
+        // L[KREG-1] (a compile-time register, no dynamic indexing).
+        uint64_t L[KR];
+#pragma unroll
+        for (int j = 0; j < KR; ++j) L[j] = (j < KR - a.k) ? ~0ull : 0ull;
+        if (KREG == 0) {
+            for (int j = 0; j < a.k; ++j) list[j] = 0ull;
+            __syncwarp();
+        }
+        const bool live = qglobal < a.B;           // padding lanes never produce candidates
+        const bool share = a.P > 1 && live;        // CTAs scanning other rows for the same query trade thresholds
+        float thr_local = live ? -INFINITY : INFINITY;
+        float thr = thr_local;
         const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(32 * (warp & 3)) << 16);
         const bool pred = a.mask != nullptr || a.ns_code != kAny || a.label_code != kAny;
         int as = 0;
@@ -322,6 +364,7 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
                 }
                 sm_scale[as * kTN + et] = sc;
             }
+            if (share) thr = fmaxf(thr_local, shared_threshold(__ldcg(a.gthr + qglobal)));
             asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
             mbar_wait(bar_tfull + 8 * as, aphase);
             tc_fence_after();
@@ -346,13 +389,57 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
                         if (row < a.n) a.dump[static_cast<size_t>(qglobal) * a.dump_ld + row] = __uint_as_float(v[j]);
                     }
                 }
-                if (any) {
+                if (KREG > 0) {
+                    if (any) {
+                        // rare: build the candidate bitmap, then handle candidates one at a time through a
+                        // single inlined insertion site (keeps the list in registers, keeps the code small)
+                        uint32_t cand = 0;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float s = __uint_as_float(v[j]);
-                        if (s > thr) {
-                            cnt = list_insert_private(list, a.k, cnt, pack_key(s, row0 + c * 32 + j));
-                            thr = cnt == a.k ? key_score(list[a.k - 1]) : -INFINITY;
+                        for (int j = 0; j < 32; ++j) cand |= (__uint_as_float(v[j]) > thr) ? (1u << j) : 0u;
+                        bool changed = false;
+                        while (cand) {
+                            const int j = __ffs(cand) - 1;
+                            cand &= cand - 1;
+                            const float s = __uint_as_float(pick32(v, j));
+                            if (s > thr) {  // thr may have risen since the bitmap was built
+                                list_insert_regs<KR>(L, pack_key(s, row0 + c * 32 + j));
+                                if (L[KR - 1] != 0ull) thr_local = key_score(L[KR - 1]);
+                                thr = fmaxf(thr, thr_local);
+                                changed = true;
+                            }
+                        }
+                        if (changed && share && L[KR - 1] != 0ull) atomicMax(a.gthr + qglobal, ord_of(thr_local));
+                    }
+                } else if (__any_sync(kFullMask, any)) {
+                    // large k: the lists live in global memory (L1/L2 resident) and the whole warp inserts
+                    // one candidate at a time (warp_list_insert: ballot-located position, parallel shift)
+                    uint32_t cand = 0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) cand |= (__uint_as_float(v[j]) > thr) ? (1u << j) : 0u;
+                    uint32_t owners = __ballot_sync(kFullMask, cand != 0u);
+                    while (owners) {
+                        const int src = __ffs(owners) - 1;
+                        owners &= owners - 1;
+                        uint32_t cm = __shfl_sync(kFullMask, cand, src);
+                        float thr_src = __shfl_sync(kFullMask, thr, src);
+                        float local_src = __shfl_sync(kFullMask, thr_local, src);
+                        uint64_t* lst = list + static_cast<ptrdiff_t>(src - lane) * a.k;  // src lane's list
+                        bool changed = false;
+                        while (cm) {
+                            const int j = __ffs(cm) - 1;
+                            cm &= cm - 1;
+                            const float s = __shfl_sync(kFullMask, __uint_as_float(pick32(v, j)), src);
+                            if (s > thr_src) {
+                                const uint64_t kth = warp_list_insert(lst, a.k, pack_key(s, row0 + c * 32 + j), lane);
+                                if (kth != 0ull) local_src = key_score(kth);
+                                thr_src = fmaxf(thr_src, local_src);
+                                changed = true;
+                            }
+                        }
+                        if (lane == src && changed) {
+                            thr_local = local_src;
+                            thr = thr_src;
+                            if (share && local_src > -INFINITY) atomicMax(a.gthr + qglobal, ord_of(local_src));
                         }
                     }
                 }
@@ -361,6 +448,11 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
             if (++as == kAccStages) { as = 0; aphase ^= 1; }
+        }
+        if (KREG > 0) {
+#pragma unroll
+            for (int j = 0; j < KR; ++j)
+                if (j >= KR - a.k) list[j - (KR - a.k)] = L[j];
         }
     }
     __syncthreads();
@@ -417,7 +509,8 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
     const int kblocks = m.Dp / kKB;
     const int n_tiles = static_cast<int>((m.n + kTN - 1) / kTN);
     const size_t smem = mma_smem_bytes(kblocks);
-    auto kernel = m.dump ? k_mma_topk<true> : k_mma_topk<false>;
+    auto kernel = m.dump ? k_mma_topk<true, 0>
+                         : (m.k <= 16 ? k_mma_topk<false, 16> : (m.k <= 32 ? k_mma_topk<false, 32> : k_mma_topk<false, 0>));
     MMA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     // batches larger than one wave of query tiles are processed in slices
     const int max_qt = m.sm_count;
@@ -429,10 +522,11 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
         int P = m.sm_count / QT;
         if (P > n_tiles) P = n_tiles;
         if (P < 1) P = 1;
-        // scratch: [Qb bf16 Bpad x Dp][lists P x Bpad x k u64][dump]
+        // scratch: [Qb bf16 Bpad x Dp][shared thresholds Bpad u32][lists P x Bpad x k u64]
         const size_t q_bytes = (static_cast<size_t>(Bpad) * m.Dp * 2 + 1023) / 1024 * 1024;
+        const size_t thr_bytes = (static_cast<size_t>(Bpad) * sizeof(uint32_t) + 1023) / 1024 * 1024;
         const size_t list_bytes = static_cast<size_t>(P) * Bpad * m.k * sizeof(uint64_t);
-        const size_t need = q_bytes + list_bytes;
+        const size_t need = q_bytes + thr_bytes + list_bytes;
         if (need > scratch.cap) {
             if (scratch.p) {
                 MMA_CUDA(cudaStreamSynchronize(m.stream));
@@ -444,10 +538,11 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
             scratch.cap = need + need / 2;
         }
         __nv_bfloat16* qb = reinterpret_cast<__nv_bfloat16*>(scratch.p);
-        uint64_t* lists = reinterpret_cast<uint64_t*>(scratch.p + q_bytes);
+        uint32_t* gthr = reinterpret_cast<uint32_t*>(scratch.p + q_bytes);
+        uint64_t* lists = reinterpret_cast<uint64_t*>(scratch.p + q_bytes + thr_bytes);
 
         k_prep_queries<<<(Bpad + 3) / 4, 128, 0, m.stream>>>(m.q + static_cast<size_t>(done) * m.D, Bs, Bpad, m.D, m.Dp,
-                                                             m.cosine ? 1 : 0, qb);
+                                                             m.cosine ? 1 : 0, qb, gthr);
         MMA_CUDA(cudaGetLastError());
 
         CUtensorMap tq, te;
@@ -470,7 +565,9 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
         a.q_tiles = QT;
         a.P = P;
         a.Bpad = Bpad;
+        a.B = Bs;
         a.lists = lists;
+        a.gthr = gthr;
         a.dump = m.dump ? m.dump + static_cast<size_t>(done) * m.dump_ld : nullptr;
         a.dump_ld = m.dump_ld;
         a.corpus_hint = QT > 1 ? kEvictNormal : kEvictFirst;

@@ -92,8 +92,9 @@ def test_distances_match_oracle(client):
     stored, scale = bf.normalise_store(x)
     s, r, c = bf.query(stored, scale, q, 10)
     for b in range(3):
-        assert res["ids"][b] == [str(i) for i in r[b]]
-        assert np.allclose(res["distances"][b], 1 - s[b], atol=1e-5)
+        # batches > 2 run on the tensor path (bf16 queries): north-star tolerance 1e-3, near-ties may swap
+        assert np.allclose(sorted(res["distances"][b]), sorted(1 - s[b]), atol=1e-3)
+        assert len(set(res["ids"][b]) & {str(i) for i in r[b]}) >= 9
 
 
 def test_upsert_replaces_vector_document_and_metadata(client):
