@@ -64,12 +64,18 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
-def traffic_for(kernel: str):
-    """dram bytes per launch from the committed ncu capture (profiles/traffic.json), else None."""
+def traffic_for(kernel: str, rows: int, dim: int, batch: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed
+    `ncu --set full` capture (profiles/traffic.json).  The capture is per launch at the captured row
+    count; DRAM traffic of a streaming scan is linear in rows, so it is scaled by rows/captured_rows
+    when the row count differs (same dim and batch only), else None."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(path):
-        return json.load(open(path)).get(kernel)
-    return None
+    if not os.path.exists(path):
+        return None
+    t = json.load(open(path)).get(kernel)
+    if not t or t.get("dim") != dim or t.get("batch") != batch:
+        return None
+    return float(t["bytes_per_launch"]) * (rows / float(t["rows"]))
 
 
 # --------------------------------------------------------------------------------------------- clocks
@@ -317,7 +323,7 @@ def run_ours(args):
         gbs = bytes_alg / (kernel_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"]}
         kernel_name = "k_scan_topk"
-    roof.update({"traffic": traffic_for(kernel_name), "kernel": kernel_name, "kernel_ms": kernel_ms,
+    roof.update({"traffic": traffic_for(kernel_name, local_rows, D, B), "kernel": kernel_name, "kernel_ms": kernel_ms,
                  "algorithmic_bytes_per_launch": bytes_alg, "peak_source": pk["source"] + " (burst; kernel timed alone)"})
 
     # ---- end to end through the host API (pinned H2D of the batch + D2H of the result every step)

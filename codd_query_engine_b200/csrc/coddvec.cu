@@ -514,7 +514,8 @@ static int upsert_impl(cv_index* idx, const int64_t* rows, const float* emb, con
         for (auto& c : idx->ctx_all) CV_CUDA(cudaStreamWaitEvent(s, c->busy, 0));
     }
 
-    const int64_t chunk_rows = std::max<int64_t>(1, std::min<int64_t>(n, (int64_t(64) << 20) / (4ll * idx->D)));
+    // host input is staged through a 64 MiB device buffer; device input is consumed in place
+    const int64_t chunk_rows = on_device ? n : std::max<int64_t>(1, std::min<int64_t>(n, (int64_t(64) << 20) / (4ll * idx->D)));
     if (!on_device) {
         if ((rc = idx->stage_x.reserve(static_cast<size_t>(chunk_rows) * idx->D))) return rc;
         if (ns_codes && (rc = idx->stage_ns.reserve(chunk_rows))) return rc;

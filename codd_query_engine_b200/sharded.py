@@ -92,7 +92,7 @@ class ShardedIndex:
                                 path=path, stream=stream)
         if self.world == 1:
             return local
-        dist.all_gather_into_tensor(gathered, local, group=self.group)  # NCCL over NVLink / NVSwitch
+        dist.all_gather_into_tensor(gathered.view(self.world * B, k), local, group=self.group)  # NCCL over NVLink
         merge_keys_device(self.device.index or 0, gathered.data_ptr(), self.world, B, k, k, merged.data_ptr(), stream)
         return merged
 

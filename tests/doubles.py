@@ -72,3 +72,33 @@ class OracleIndex:
 
     def stats(self):
         return None
+
+
+# ---- pointer-based entry points (used by sharded.ShardedIndex with CPU tensors under gloo) ----
+def _view(ptr, shape, dtype):
+    import ctypes
+
+    n = int(np.prod(shape))
+    buf = (ctypes.c_char * (n * np.dtype(dtype).itemsize)).from_address(int(ptr))
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+
+def _query_device(self, q_ptr, B, k, out_keys_ptr, ns_code=bf.ANY_CODE, label_code=bf.ANY_CODE, mask_ptr=0, path=0,
+                  stream=None):
+    q = _view(q_ptr, (B, self.dim), np.float32)
+    s, r, c = self.query(q, k, ns_code=ns_code, label_code=label_code)
+    keys = np.where(r >= 0, bf.pack_keys(s.ravel(), np.maximum(r, 0).ravel()).reshape(r.shape), np.uint64(0))
+    _view(out_keys_ptr, (B, k), np.uint64)[...] = keys
+
+
+def _upsert_device(self, emb_ptr, n, rows=None, ns_ptr=0, label_ptr=0):
+    return self.upsert(_view(emb_ptr, (n, self.dim), np.float32).copy(), rows=rows)
+
+
+OracleIndex.query_device = _query_device
+OracleIndex.upsert_device = _upsert_device
+
+
+def oracle_merge_keys_device(device, keys_in_ptr, G, B, k_in, k_out, out_ptr, stream=0):
+    keys = _view(keys_in_ptr, (G, B, k_in), np.uint64)
+    _view(out_ptr, (B, k_out), np.uint64)[...] = bf.merge_keys(keys, k_out)
