@@ -1,0 +1,79 @@
+"""Run the REFERENCE's own store tests (unmodified files under /root/reference/tests) against this
+package used as a drop-in `chromadb` (shim/ on sys.path).  Build-container only; executed in a
+subprocess by tests/test_dropin_reference.py.
+
+    python tests/run_reference_tests_dropin.py [--native]
+
+Without --native the vector index is the oracle-backed test double (no GPU here); with --native (GPU box
+with the reference tree available) it is libcoddvec.so.
+"""
+import importlib.abc
+import importlib.machinery
+import importlib.util
+import inspect
+import os
+import sys
+import types
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("CODD_REFERENCE", "/root/reference")
+MISSING_OK = ("opus_agent_base", "pydantic_ai", "logfire", "rapidfuzz", "redis", "fakeredis")
+
+
+class _StubFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    """Empty stand-ins for third-party packages the reference imports but this image lacks
+    (none of them is on the semantic-store path)."""
+
+    def find_spec(self, name, path=None, target=None):
+        if name.split(".")[0] in MISSING_OK:
+            return importlib.machinery.ModuleSpec(name, self, is_package=True)
+        return None
+
+    def create_module(self, spec):
+        mod = types.ModuleType(spec.name)
+        mod.__path__ = []
+        mod.__getattr__ = lambda attr: type(attr, (), {})  # any attribute -> a dummy class
+        return mod
+
+    def exec_module(self, module):
+        pass
+
+
+def main():
+    sys.path[:0] = [os.path.join(ROOT, "shim"), ROOT, REF]
+    sys.meta_path.append(_StubFinder())
+    if "--native" not in sys.argv:
+        from codd_query_engine_b200 import client as client_mod
+        from tests.doubles import OracleIndex
+
+        client_mod.NativeIndex = OracleIndex
+    import chromadb  # noqa: F401  (the shim)
+
+    assert chromadb.__version__ == "coddvec-shim"
+    ran = 0
+    for rel, cls_name in (
+        ("tests/unit/codd_dal/metrics/test_metrics_semantic_metadata_store.py", "TestMetricsSemanticMetadataStore"),
+        ("tests/integration/codd_dal/metrics/test_metrics_semantic_metadata_store_integration.py",
+         "TestMetricsSemanticMetadataStoreIntegration"),
+    ):
+        spec = importlib.util.spec_from_file_location("ref_" + cls_name, os.path.join(REF, rel))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)  # imports the reference's MetricsSemanticMetadataStore + `chromadb`
+        store_cls = mod.MetricsSemanticMetadataStore
+        assert store_cls.__module__ == "codd_dal.metrics.metrics_semantic_metadata_store"
+        suite = getattr(mod, cls_name)()
+        for name, fn in inspect.getmembers(suite, predicate=inspect.ismethod):
+            if not name.startswith("test_"):
+                continue
+            client = chromadb.EphemeralClient()              # what the reference's fixture builds
+            store = store_cls(client, collection_name=f"test_{name}")
+            fn(store)
+            client.delete_collection(f"test_{name}")
+            ran += 1
+            print("PASS", rel.split("/")[-1], name)
+    print(f"reference tests passed against the drop-in: {ran}")
+    assert ran == 9, ran
+
+
+if __name__ == "__main__":
+    main()
