@@ -1,0 +1,137 @@
+#!/usr/bin/env python
+"""Secondary BASELINE.json configs on one B200 (bench.py covers configs[1] and the 100M corpus):
+
+  cfg3  10M x 768 bf16, fused namespace predicate at 10 % selectivity, top-50, batch 1 (K2 PRED)
+  cfg5  bulk upsert of 1M x 384 fp32 host embeddings in chunks of 1000 (MAX_BULK_OPERATIONS,
+        codd_dal/metrics/metrics_semantic_metadata_store.py:23) interleaved with live top-10 queries
+
+Each result is parity-checked against the oracle (checker only) and printed as one JSON line.
+    python tools/bench_configs.py [cfg3] [cfg5] [--rows3 N] [--rows5 N]
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+import bench  # noqa: E402  (peaks, C oracle loader)
+from codd_query_engine_b200 import native  # noqa: E402
+from oracle import brute_force as bf  # noqa: E402  (checker only)
+
+
+def arg(name, default):
+    return int(sys.argv[sys.argv.index(name) + 1]) if name in sys.argv else default
+
+
+def time_device(fn, iters, warm=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def cfg3(rows):
+    D, k, sel_ns = 768, 50, 7
+    pk = bench.peaks()
+    idx = native.NativeIndex(D, capacity_rows=rows, max_rows=rows)
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    ns_all = []
+    for lo in range(0, rows, 500_000):
+        m = min(500_000, rows - lo)
+        x = torch.randn((m, D), device="cuda", generator=gen)
+        # 10 namespaces, the target one holds exactly 10 % of every chunk
+        ns = (torch.arange(m, device="cuda") % 10 + 1).to(torch.int32)
+        ns = ns[torch.randperm(m, device="cuda", generator=gen)].contiguous()
+        idx.upsert_device(x.data_ptr(), m, ns_ptr=ns.data_ptr())
+        ns_all.append(ns.cpu().numpy().astype(np.uint32))
+    del x
+    ns_all = np.concatenate(ns_all)
+    q = torch.randn((1, D), device="cuda", generator=gen)
+    out = torch.zeros((1, k), dtype=torch.int64, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    ms_pred = time_device(lambda: idx.query_device(q.data_ptr(), 1, k, out.data_ptr(), ns_code=sel_ns, stream=s), 50)
+    keys_pred = out.cpu().numpy().view(np.uint64).copy()
+    ms_full = time_device(lambda: idx.query_device(q.data_ptr(), 1, k, out.data_ptr(), stream=s), 20)
+    n_sel = int((ns_all == sel_ns).sum())
+    st = idx.stats()
+    sel_bytes = n_sel * (2 * st.dim_padded + 4) + rows * 4  # selected rows + the namespace column
+    # parity: oracle over the eligible rows only (same stored embeddings)
+    el = np.nonzero(ns_all == sel_ns)[0]
+    stored, scale, _, _ = idx.get_rows(el)
+    es, er, ec = bf.query(stored, scale, q.cpu().numpy(), k)
+    gs, gr = native.decode_keys(keys_pred)
+    parity = bool(np.array_equal(gr[0], el[er[0]]) and np.abs(gs - es).max() <= 2e-6)
+    idx.close()
+    return {"config": "cfg3", "workload": f"{rows} x 768 bf16, namespace predicate {n_sel / rows:.3f} selectivity, top-{k}, batch 1",
+            "ms_per_query": ms_pred, "qps": 1e3 / ms_pred, "selected_rows": n_sel,
+            "selected_bytes_gbs": sel_bytes / ms_pred / 1e6, "selected_bytes_frac_of_hbm": sel_bytes / ms_pred / 1e6 / pk["hbm_gbs"],
+            "logical_scan_gbs": rows * (2 * st.dim_padded + 4) / ms_pred / 1e6,
+            "unfiltered_ms_per_query": ms_full, "unfiltered_gbs": rows * (2 * st.dim_padded + 4) / ms_full / 1e6,
+            "parity_vs_oracle": parity}
+
+
+def cfg5(rows):
+    D, k, chunk = 384, 10, 1000
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((rows, D), dtype=np.float32)
+    q = rng.standard_normal((1, D), dtype=np.float32)
+    idx = native.NativeIndex(D, capacity_rows=rows, max_rows=rows)
+    idx.upsert(x[:chunk])  # warm the path
+    lat, t_up = [], 0.0
+    t0 = time.perf_counter()
+    for lo in range(chunk, rows, chunk):
+        a = time.perf_counter()
+        idx.upsert(x[lo:lo + chunk])
+        b = time.perf_counter()
+        t_up += b - a
+        if (lo // chunk) % 10 == 0:  # a live top-10 query every 10 chunks, over the growing corpus
+            idx.query(q, k)
+            lat.append(time.perf_counter() - b)
+    wall = time.perf_counter() - t0
+    # one bulk call for comparison (what a batched indexer would issue)
+    idx2 = native.NativeIndex(D, capacity_rows=rows, max_rows=rows)
+    a = time.perf_counter()
+    idx2.upsert(x)
+    bulk = time.perf_counter() - a
+    # parity of the final state: stored bits == oracle K1, final query == oracle
+    s, r, c = idx.query(q, k)
+    sample = np.arange(0, rows, max(1, rows // 100_000))
+    stored, scale, _, _ = idx.get_rows(sample)
+    est, esc = bf.normalise_store(x[sample])
+    k1_exact = bool(np.array_equal(stored, est) and np.array_equal(scale, esc))
+    lib = bench.load_c_oracle()
+    allst, allsc, _, _ = idx.get_rows(np.arange(rows))
+    _, _, okeys = bench.cpu_time_queries(lib, allst, allsc, q, k, 1)
+    os_, or_ = bf.unpack_keys(okeys)
+    parity = bool(np.array_equal(or_, r) and np.abs(os_ - s).max() <= 2e-6)
+    idx.close()
+    idx2.close()
+    lat = np.array(lat) * 1e3
+    return {"config": "cfg5", "workload": f"{rows} x 384 fp32 host embeddings upserted in chunks of {chunk}, top-10 query every 10 chunks",
+            "rows_per_s_chunked": (rows - chunk) / t_up, "wall_s_interleaved": wall, "queries": int(lat.size),
+            "query_ms_p50": float(np.percentile(lat, 50)), "query_ms_p99": float(np.percentile(lat, 99)),
+            "rows_per_s_single_bulk_call": rows / bulk, "h2d_gbs_single_bulk_call": rows * D * 4 / bulk / 1e9,
+            "k1_bit_exact": k1_exact, "final_query_parity_vs_oracle": parity}
+
+
+def main():
+    want = [a for a in sys.argv[1:] if a.startswith("cfg")] or ["cfg3", "cfg5"]
+    if "cfg3" in want:
+        print(json.dumps(cfg3(arg("--rows3", 10_000_000))), flush=True)
+    if "cfg5" in want:
+        print(json.dumps(cfg5(arg("--rows5", 1_000_000))), flush=True)
+
+
+if __name__ == "__main__":
+    main()
