@@ -279,8 +279,12 @@ int enqueue_query(cv_index* idx, QueryCtx* c, cudaStream_t stream, const float* 
     if (timed) CV_CUDA(cudaEventRecord(c->t0, stream));
     int64_t passes_bytes = 0;
 
+    int variant = 0;
+    if (path == CV_PATH_MMA_1CTA) { variant = 1; path = CV_PATH_MMA; }
+    if (path == CV_PATH_MMA_2CTA) { variant = 2; path = CV_PATH_MMA; }
     if (path == CV_PATH_MMA) {
         MmaArgs m;
+        m.variant = variant;
         m.E = idx->E.ptr<void>();
         m.scale = idx->scale.ptr<float>();
         m.ns = idx->ns.ptr<uint32_t>();
@@ -361,7 +365,7 @@ int check_query_params(const cv_index* idx, const void* q, const cv_query_params
     if (!idx || !q || !p) return fail(CV_ERR_INVALID, "null argument");
     if (p->n_queries < 1) return fail(CV_ERR_INVALID, "n_queries must be >= 1 (got %d)", p->n_queries);
     if (p->k < 1 || p->k > CV_MAX_K) return fail(CV_ERR_INVALID, "k must be in [1, %d] (got %d)", CV_MAX_K, p->k);
-    if (p->path != CV_PATH_AUTO && p->path != CV_PATH_SCAN && p->path != CV_PATH_MMA)
+    if (p->path < CV_PATH_AUTO || p->path > CV_PATH_MMA_2CTA)
         return fail(CV_ERR_INVALID, "unknown path %d", p->path);
     return CV_OK;
 }
@@ -672,8 +676,10 @@ cudaError_t launch_merge_keys(const uint64_t* in, int G, int b_stride, int k_in,
 
 extern "C" {
 
-int cv_debug_mma_scores(cv_index* idx, const float* q, int32_t B, float* out_scores) {
+int cv_debug_mma_scores(cv_index* idx, const float* q, int32_t B, int32_t path, float* out_scores) {
     if (!idx || !q || !out_scores || B < 1) return fail(CV_ERR_INVALID, "bad argument");
+    if (path != CV_PATH_MMA && path != CV_PATH_MMA_1CTA && path != CV_PATH_MMA_2CTA)
+        return fail(CV_ERR_INVALID, "path must be one of the tensor-core paths");
     DeviceGuard dg(idx->cfg.device);
     if (!dg.ok) return fail(CV_ERR_CUDA, "cudaSetDevice(%d) failed", idx->cfg.device);
     const int64_t n = idx->n_committed.load(std::memory_order_acquire);
@@ -688,7 +694,7 @@ int cv_debug_mma_scores(cv_index* idx, const float* q, int32_t B, float* out_sco
     } rel{idx, c};
     cudaStream_t s = c->stream;
     CV_CUDA(cudaStreamWaitEvent(s, c->busy, 0));
-    const int Bpad = (B + 127) / 128 * 128;
+    const int Bpad = (B + 255) / 256 * 256;
     DevBuf<float> d_dump, d_q;
     DevBuf<uint64_t> d_out;
     if ((rc = d_dump.reserve(static_cast<size_t>(Bpad) * n)) || (rc = d_q.reserve(static_cast<size_t>(B) * idx->D)) ||
@@ -702,7 +708,7 @@ int cv_debug_mma_scores(cv_index* idx, const float* q, int32_t B, float* out_sco
     p.ns_code = CV_ANY;
     p.label_code = CV_ANY;
     p.mask = nullptr;
-    p.path = CV_PATH_MMA;
+    p.path = path;
     rc = enqueue_query(idx, c, s, d_q.p, &p, nullptr, d_out.p, d_dump.p, n);
     if (rc) { (void)cudaStreamSynchronize(s); return rc; }
     CV_CUDA(cudaMemcpyAsync(out_scores, d_dump.p, sizeof(float) * B * n, cudaMemcpyDeviceToHost, s));

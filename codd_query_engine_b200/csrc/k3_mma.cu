@@ -102,35 +102,94 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
+// CG = 2: issued by both CTAs of the pair; the peer bit of the barrier address is cleared so that the
+// transaction bytes are counted on the LEADER's barrier (the MMA issuer waits there for both halves).
+template <int CG>
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, uint64_t hint) {
+    if (CG == 1) {
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+            " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+            "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "l"(hint)
+            : "memory");
+    } else {
+        asm volatile(
+            "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+            " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+            "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "l"(hint)
+            : "memory");
+    }
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of this cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-        " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
-        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "l"(hint)
+        "{\n\t"
+        ".reg .b32 remote;\n\t"
+        "mapa.shared::cluster.u32 remote, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [remote];\n\t"
+        "}\n" ::"r"(bar), "r"(cta)
         : "memory");
 }
 
+template <int CG>
 __device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CG == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
 }
+template <int CG>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+    if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
 // D[tmem] (+)= A[smem desc] * B[smem desc]^T, bf16 x bf16 -> fp32, issued by one thread for the CTA
+template <int CG>
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
+    if (CG == 1) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+            "}\n" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+            "}\n" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
 }
 // arrive on an mbarrier when every tcgen05.mma issued so far by this thread has completed
+// (CG = 2: on the barrier at this offset in BOTH CTAs of the pair)
+template <int CG>
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    if (CG == 1) {
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    } else {
+        const uint16_t mask = 3;
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                     "h"(mask)
+                     : "memory");
+    }
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -234,100 +293,116 @@ __global__ void __launch_bounds__(128) k_prep_queries(const float* q, int B, int
 }
 
 // ------------------------------------------------------------------------------------------ main kernel
-template <bool DUMP, int KREG>
+// CG = 1: one CTA per SM works alone (M = 128 queries, N = 128 corpus rows per tile).
+// CG = 2: a CTA pair (cluster of 2, `cta_group::2`) shares every MMA: M = 256 queries (128 per CTA),
+//         N = 256 corpus rows per tile of which each CTA stages 128 -- so each SM reads half the B
+//         operand from its shared memory and L2 serves each corpus tile once per 256 queries.
+//         Only the leader CTA (cluster rank 0) issues MMAs; both CTAs' TMA loads complete on the
+//         leader's `full` barrier; `tcgen05.commit ... multicast` releases ring slots / publishes
+//         accumulators in both CTAs; the peer's epilogue warps arrive remotely on the leader's
+//         `tmem_empty` barrier.
+template <bool DUMP, int KREG, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_e, const KArgs a) {
+    constexpr int TN = kTN * CG;                       // corpus rows (= accumulator columns) per tile
+    constexpr uint32_t kCols = kAccStages * TN;        // TMEM columns: 256 (CG=1) / 512 (CG=2)
     extern __shared__ __align__(1024) unsigned char smem[];
     // carve-up (all block bases 1024-byte aligned, as SWIZZLE_128B requires)
-    unsigned char* sm_q = smem;                                           // kblocks x 16 KiB
-    unsigned char* sm_ring = smem + static_cast<size_t>(a.kblocks) * kBlockBytes;  // kStages x 16 KiB
-    float* sm_scale = reinterpret_cast<float*>(sm_ring + static_cast<size_t>(kStages) * kBlockBytes);  // [2][128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sm_scale + kAccStages * kTN);
+    unsigned char* sm_q = smem;                                           // kblocks x 16 KiB (own 128 queries)
+    unsigned char* sm_ring = smem + static_cast<size_t>(a.kblocks) * kBlockBytes;  // kStages x 16 KiB (own 128 rows)
+    float* sm_scale = reinterpret_cast<float*>(sm_ring + static_cast<size_t>(kStages) * kBlockBytes);  // [2][TN]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm_scale + kAccStages * TN);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1 + 2 * kAccStages);
 
-    const uint32_t bar_full = smem_u32(bars);                  // [kStages]
+    const uint32_t bar_full = smem_u32(bars);                  // [kStages]   (leader's are the live ones)
     const uint32_t bar_empty = bar_full + 8 * kStages;         // [kStages]
     const uint32_t bar_q = bar_empty + 8 * kStages;            // [1]
     const uint32_t bar_tfull = bar_q + 8;                      // [kAccStages]
-    const uint32_t bar_tempty = bar_tfull + 8 * kAccStages;    // [kAccStages]
+    const uint32_t bar_tempty = bar_tfull + 8 * kAccStages;    // [kAccStages] (leader's are the live ones)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int qt = blockIdx.x % a.q_tiles;
-    const int p = blockIdx.x / a.q_tiles;
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;   // 0 = leader
+    const int unit = blockIdx.x / CG;                         // CTA (CG=1) or CTA pair (CG=2)
+    const int qt = unit % a.q_tiles;                          // query tile of 128*CG queries
+    const int p = unit / a.q_tiles;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
-            mbar_init(bar_full + 8 * s, 1);
-            mbar_init(bar_empty + 8 * s, 1);
+            mbar_init(bar_full + 8 * s, CG);      // own arrive.expect_tx (+ the peer's remote arrive)
+            mbar_init(bar_empty + 8 * s, 1);      // one tcgen05.commit
         }
-        mbar_init(bar_q, 1);
+        mbar_init(bar_q, CG);
         for (int s = 0; s < kAccStages; ++s) {
             mbar_init(bar_tfull + 8 * s, 1);
-            mbar_init(bar_tempty + 8 * s, 4);  // one arrival per epilogue warp
+            mbar_init(bar_tempty + 8 * s, 4 * CG);  // one arrival per epilogue warp of every CTA in the group
         }
         fence_barrier_init();
         fence_proxy_async();
     }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+    if (warp == 1) tmem_alloc<CG>(smem_u32(tmem_slot), kCols);
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================================================================== TMA producer
+        // ===================================================================== TMA producer (every CTA)
         if (lane == 0) {
             tma_prefetch_desc(&tmap_q);
             tma_prefetch_desc(&tmap_e);
-            mbar_arrive_expect_tx(bar_q, static_cast<uint32_t>(a.kblocks) * kBlockBytes);
+            const uint32_t q_bytes = static_cast<uint32_t>(a.kblocks) * kBlockBytes;
+            if (rank == 0) mbar_arrive_expect_tx(bar_q, q_bytes * CG);
+            else mbar_arrive_cluster(bar_q, 0);
             for (int kb = 0; kb < a.kblocks; ++kb)
-                tma_load_2d(smem_u32(sm_q + static_cast<size_t>(kb) * kBlockBytes), &tmap_q, bar_q, kb * kKB, qt * kQ, kEvictLast);
+                tma_load_2d<CG>(smem_u32(sm_q + static_cast<size_t>(kb) * kBlockBytes), &tmap_q, bar_q, kb * kKB,
+                                (qt * CG + static_cast<int>(rank)) * kQ, kEvictLast);
             int stage = 0;
             uint32_t phase = 0;
             for (int t = p; t < a.n_tiles; t += a.P) {
                 for (int kb = 0; kb < a.kblocks; ++kb) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                    mbar_arrive_expect_tx(bar_full + 8 * stage, kBlockBytes);
-                    tma_load_2d(smem_u32(sm_ring + static_cast<size_t>(stage) * kBlockBytes), &tmap_e, bar_full + 8 * stage,
-                                kb * kKB, t * kTN, a.corpus_hint);
+                    if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, kBlockBytes * CG);
+                    else mbar_arrive_cluster(bar_full + 8 * stage, 0);
+                    tma_load_2d<CG>(smem_u32(sm_ring + static_cast<size_t>(stage) * kBlockBytes), &tmap_e,
+                                    bar_full + 8 * stage, kb * kKB, t * TN + static_cast<int>(rank) * kTN, a.corpus_hint);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================================================================== MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(kQ, kTN);
+        // ===================================================================== MMA issuer (leader CTA only)
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(kQ * CG, TN);
             mbar_wait(bar_q, 0);
             tc_fence_after();
             int stage = 0, as = 0;
             uint32_t phase = 0, aphase = 0;
             for (int t = p; t < a.n_tiles; t += a.P) {
-                mbar_wait(bar_tempty + 8 * as, aphase ^ 1);  // epilogue has drained this accumulator stage
+                mbar_wait(bar_tempty + 8 * as, aphase ^ 1);  // every epilogue warp has drained this accumulator stage
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * kTN);
+                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * TN);
                 for (int kb = 0; kb < a.kblocks; ++kb) {
-                    mbar_wait(bar_full + 8 * stage, phase);  // TMA bytes have landed
+                    mbar_wait(bar_full + 8 * stage, phase);  // TMA bytes of every CTA in the group have landed
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(sm_q + static_cast<size_t>(kb) * kBlockBytes);
                     const uint32_t b_addr = smem_u32(sm_ring + static_cast<size_t>(stage) * kBlockBytes);
 #pragma unroll
                     for (int ks = 0; ks < kKB / 16; ++ks)  // UMMA_K = 16 bf16 = 32 bytes inside the swizzle row
-                        umma_bf16(tmem_d, umma_desc_sw128(a_addr + ks * 32), umma_desc_sw128(b_addr + ks * 32), idesc,
-                                  (kb | ks) != 0 ? 1u : 0u);
-                    umma_commit(bar_empty + 8 * stage);  // frees the ring slot once these MMAs have read it
+                        umma_bf16<CG>(tmem_d, umma_desc_sw128(a_addr + ks * 32), umma_desc_sw128(b_addr + ks * 32), idesc,
+                                      (kb | ks) != 0 ? 1u : 0u);
+                    umma_commit<CG>(bar_empty + 8 * stage);  // frees the ring slot (in both CTAs) once read
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(bar_tfull + 8 * as);  // accumulator complete -> epilogue
+                umma_commit<CG>(bar_tfull + 8 * as);  // accumulator complete -> epilogue warps (of both CTAs)
                 if (++as == kAccStages) { as = 0; aphase ^= 1; }
             }
         }
     } else {
-        // ===================================================================== epilogue (128 threads)
-        const int et = threadIdx.x - 64;                 // 0..127: column this thread stages scale for
-        const int qlane = 32 * (warp & 3) + lane;        // TMEM lane = query within the tile
-        const int qglobal = qt * kQ + qlane;
+        // ===================================================================== epilogue (128 threads per CTA)
+        const int et = threadIdx.x - 64;                 // 0..127
+        const int qlane = 32 * (warp & 3) + lane;        // TMEM lane = query within this CTA's 128
+        const int qglobal = (qt * CG + static_cast<int>(rank)) * kQ + qlane;
         uint64_t* list = a.lists + (static_cast<size_t>(p) * a.Bpad + qglobal) * a.k;
         constexpr int KR = KREG > 0 ? KREG : 1;
         // k <= KREG: the list lives in registers, right-aligned -- slots [KREG-k, KREG) hold the top-k
@@ -349,9 +424,10 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
         int as = 0;
         uint32_t aphase = 0;
         for (int t = p; t < a.n_tiles; t += a.P) {
-            // stage scale * eligibility for this tile's 128 rows (NaN = skip)
-            {
-                const int64_t row = static_cast<int64_t>(t) * kTN + et;
+            // stage scale * eligibility for this tile's TN rows (NaN = skip)
+#pragma unroll
+            for (int h = 0; h < CG; ++h) {
+                const int64_t row = static_cast<int64_t>(t) * TN + h * kTN + et;
                 float sc = __int_as_float(0x7FC00000);
                 if (row < a.n) {
                     bool ok = true;
@@ -362,18 +438,18 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
                     }
                     if (ok) sc = __ldg(a.scale + row);
                 }
-                sm_scale[as * kTN + et] = sc;
+                sm_scale[as * TN + h * kTN + et] = sc;
             }
             if (share) thr = fmaxf(thr_local, shared_threshold(__ldcg(a.gthr + qglobal)));
-            asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
+            asm volatile("bar.sync 1, 128;" ::: "memory");  // this CTA's epilogue warps only
             mbar_wait(bar_tfull + 8 * as, aphase);
             tc_fence_after();
-            const float* sc_tile = sm_scale + as * kTN;
-            const uint32_t row0 = a.row_offset + static_cast<uint32_t>(t) * kTN;
+            const float* sc_tile = sm_scale + as * TN;
+            const uint32_t row0 = a.row_offset + static_cast<uint32_t>(t) * TN;
 #pragma unroll 1
-            for (int c = 0; c < kTN / 32; ++c) {
+            for (int c = 0; c < TN / 32; ++c) {
                 uint32_t v[32];
-                tmem_ld32(lane_base + static_cast<uint32_t>(as * kTN + c * 32), v);
+                tmem_ld32(lane_base + static_cast<uint32_t>(as * TN + c * 32), v);
                 tmem_ld_wait();
                 bool any = false;
 #pragma unroll
@@ -385,7 +461,7 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
                 if (DUMP) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const int64_t row = static_cast<int64_t>(t) * kTN + c * 32 + j;
+                        const int64_t row = static_cast<int64_t>(t) * TN + c * 32 + j;
                         if (row < a.n) a.dump[static_cast<size_t>(qglobal) * a.dump_ld + row] = __uint_as_float(v[j]);
                     }
                 }
@@ -446,7 +522,10 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+            if (lane == 0) {
+                if (rank == 0) mbar_arrive(bar_tempty + 8 * as);
+                else mbar_arrive_cluster(bar_tempty + 8 * as, 0);
+            }
             if (++as == kAccStages) { as = 0; aphase ^= 1; }
         }
         if (KREG > 0) {
@@ -455,16 +534,27 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
                 if (j >= KR - a.k) list[j - (KR - a.k)] = L[j];
         }
     }
-    __syncthreads();
+    tc_fence_before();
+    if (CG == 2) cluster_sync(); else __syncthreads();  // nobody leaves while its partner may still touch it
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        tmem_dealloc<CG>(tmem_base, kCols);
     }
 }
 
-size_t mma_smem_bytes(int kblocks) {
-    return static_cast<size_t>(kblocks + kStages) * kBlockBytes + kAccStages * kTN * sizeof(float) +
+size_t mma_smem_bytes(int kblocks, int cg) {
+    return static_cast<size_t>(kblocks + kStages) * kBlockBytes + kAccStages * kTN * cg * sizeof(float) +
            (2 * kStages + 1 + 2 * kAccStages) * sizeof(uint64_t) + 16;
+}
+
+using MmaKernel = void (*)(const CUtensorMap, const CUtensorMap, const KArgs);
+
+template <int CG>
+MmaKernel pick_mma_kernel(bool dump, int k) {
+    if (dump) return k_mma_topk<true, 0, CG>;
+    if (k <= 16) return k_mma_topk<false, 16, CG>;
+    if (k <= 32) return k_mma_topk<false, 32, CG>;
+    return k_mma_topk<false, 0, CG>;
 }
 
 thread_local std::string g_mma_err;
@@ -507,19 +597,22 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
     if (!mma_supported(m.Dp))
         return mma_fail(CV_ERR_UNSUPPORTED, "tensor-core path supports padded dim <= 512 (got " + std::to_string(m.Dp) + ")");
     const int kblocks = m.Dp / kKB;
-    const int n_tiles = static_cast<int>((m.n + kTN - 1) / kTN);
-    const size_t smem = mma_smem_bytes(kblocks);
-    auto kernel = m.dump ? k_mma_topk<true, 0>
-                         : (m.k <= 16 ? k_mma_topk<false, 16> : (m.k <= 32 ? k_mma_topk<false, 32> : k_mma_topk<false, 0>));
+    // CTA pairs (cta_group::2, 256 queries x 256 rows per tile) once a batch fills more than one
+    // 128-query tile; single CTAs below that (the scan is HBM-bound there and pairs would idle lanes).
+    const int cg = m.variant == 1 ? 1 : (m.variant == 2 ? 2 : (m.B > kQ ? 2 : 1));
+    const int tile_rows = kTN * cg, tile_q = kQ * cg;
+    const int n_tiles = static_cast<int>((m.n + tile_rows - 1) / tile_rows);
+    const int units = m.sm_count / cg;  // CTAs or CTA pairs that fit the chip
+    const size_t smem = mma_smem_bytes(kblocks, cg);
+    MmaKernel kernel = cg == 2 ? pick_mma_kernel<2>(m.dump != nullptr, m.k) : pick_mma_kernel<1>(m.dump != nullptr, m.k);
     MMA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     // batches larger than one wave of query tiles are processed in slices
-    const int max_qt = m.sm_count;
     int done = 0;
     while (done < m.B) {
-        const int Bs = std::min(m.B - done, max_qt * kQ);
-        const int QT = (Bs + kQ - 1) / kQ;
-        const int Bpad = QT * kQ;
-        int P = m.sm_count / QT;
+        const int Bs = std::min(m.B - done, units * tile_q);
+        const int QT = (Bs + tile_q - 1) / tile_q;
+        const int Bpad = QT * tile_q;
+        int P = units / QT;
         if (P > n_tiles) P = n_tiles;
         if (P < 1) P = 1;
         // scratch: [Qb bf16 Bpad x Dp][shared thresholds Bpad u32][lists P x Bpad x k u64]
@@ -571,8 +664,20 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
         a.dump = m.dump ? m.dump + static_cast<size_t>(done) * m.dump_ld : nullptr;
         a.dump_ld = m.dump_ld;
         a.corpus_hint = QT > 1 ? kEvictNormal : kEvictFirst;
-        kernel<<<QT * P, kThreads, smem, m.stream>>>(tq, te, a);
-        MMA_CUDA(cudaGetLastError());
+
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(static_cast<unsigned>(QT * P * cg));
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = m.stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = static_cast<unsigned>(cg);
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        MMA_CUDA(cudaLaunchKernelEx(&cfg, kernel, tq, te, a));
         MMA_CUDA(launch_merge_keys(lists, P, Bpad, m.k, m.k, m.out + static_cast<size_t>(done) * m.k, Bs, m.stream));
         if (launches) launches->fetch_add(3);
         done += Bs;

@@ -30,6 +30,7 @@ struct MmaArgs {
     int64_t dump_ld;
     unsigned int* counter;
     int sm_count;
+    int variant;            // 0 = pick by batch size, 1 = single-CTA tiles, 2 = CTA pairs (cta_group::2)
     cudaStream_t stream;
 };
 

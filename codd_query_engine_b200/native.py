@@ -32,6 +32,8 @@ MAX_DIM = 4096
 PATH_AUTO = 0
 PATH_SCAN = 1
 PATH_MMA = 2
+PATH_MMA_1CTA = 3
+PATH_MMA_2CTA = 4
 
 LIB_NAME = "libcoddvec.so"
 
@@ -116,7 +118,7 @@ def load_library() -> ctypes.CDLL:
         "cv_decode_keys": (None, [vp, i64, vp, vp]),
         "cv_encode_key": (u64, [ctypes.c_float, u32]),
         "cv_get_rows": (ctypes.c_int, [vp, vp, i64, vp, vp, vp, vp]),
-        "cv_debug_mma_scores": (ctypes.c_int, [vp, vp, i32, vp]),
+        "cv_debug_mma_scores": (ctypes.c_int, [vp, vp, i32, i32, vp]),
         "cv_count": (i64, [vp]),
         "cv_dim": (i32, [vp]),
         "cv_set_profiling": (ctypes.c_int, [vp, i32]),
@@ -285,11 +287,11 @@ class NativeIndex:
         _check(self._lib.cv_get_rows(self._h, _ptr(r), n, _ptr(vec), _ptr(scale), _ptr(ns), _ptr(lb)))
         return vec, scale, ns, lb
 
-    def debug_mma_scores(self, queries: np.ndarray) -> np.ndarray:
+    def debug_mma_scores(self, queries: np.ndarray, path: int = PATH_MMA) -> np.ndarray:
         """Every score the tensor-core path computes: [B][count] fp32 (testing aid)."""
         q = np.ascontiguousarray(queries, dtype=np.float32)
         out = np.empty((q.shape[0], len(self)), dtype=np.float32)
-        _check(self._lib.cv_debug_mma_scores(self._h, _ptr(q), q.shape[0], _ptr(out)))
+        _check(self._lib.cv_debug_mma_scores(self._h, _ptr(q), q.shape[0], int(path), _ptr(out)))
         return out
 
     def set_profiling(self, enabled: bool) -> None:

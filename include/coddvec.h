@@ -55,7 +55,9 @@ extern "C" {
 
 #define CV_PATH_AUTO 0 /* pick by batch size */
 #define CV_PATH_SCAN 1 /* K2: CUDA-core HBM streaming scan (small batches) */
-#define CV_PATH_MMA 2  /* K3: TMA + tcgen05 tensor-core scoring (batched) */
+#define CV_PATH_MMA 2  /* K3: TMA + tcgen05 tensor-core scoring (batched); CTA pairs when B > 128 */
+#define CV_PATH_MMA_1CTA 3 /* K3 forced to single-CTA tiles (cta_group::1, 128 queries x 128 rows) */
+#define CV_PATH_MMA_2CTA 4 /* K3 forced to CTA pairs (cta_group::2, 256 queries x 256 rows) */
 
 typedef struct cv_index cv_index;
 
@@ -134,8 +136,9 @@ int cv_get_rows(cv_index* idx, const int64_t* rows, int64_t n, uint16_t* out_bf1
                 uint32_t* out_ns, uint32_t* out_label);
 
 /* Testing aid: run the tensor-core path (K3) for B queries and return EVERY score it computed,
- * out_scores[B][count] (host), so that tests can compare the whole score matrix with the oracle. */
-int cv_debug_mma_scores(cv_index* idx, const float* q, int32_t B, float* out_scores);
+ * out_scores[B][count] (host), so that tests can compare the whole score matrix with the oracle.
+ * path: CV_PATH_MMA, CV_PATH_MMA_1CTA or CV_PATH_MMA_2CTA. */
+int cv_debug_mma_scores(cv_index* idx, const float* q, int32_t B, int32_t path, float* out_scores);
 
 int64_t cv_count(const cv_index* idx);
 int32_t cv_dim(const cv_index* idx);

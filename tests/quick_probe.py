@@ -28,7 +28,8 @@ def main():
         for pname in paths:
             if pname == "scan" and B > 16:
                 continue
-            path = native.PATH_SCAN if pname == "scan" else native.PATH_MMA
+            path = {"scan": native.PATH_SCAN, "mma": native.PATH_MMA, "mma1": native.PATH_MMA_1CTA,
+                    "mma2": native.PATH_MMA_2CTA}[pname]
             fn = lambda: idx.query_device(q.data_ptr(), B, k, out.data_ptr(), path=path, stream=s)  # noqa: E731
             for _ in range(3):
                 fn()
@@ -43,7 +44,7 @@ def main():
             ms = e0.elapsed_time(e1) / iters
             gb = rows * (2 * D + 4) / 1e9
             tf = 2.0 * B * rows * D / 1e12
-            print(f"D={D} rows={rows} B={B:5d} {pname:4s}: {ms:9.4f} ms  {B / ms * 1e3:12.0f} qps  "
+            print(f"D={D} rows={rows} k={k} B={B:5d} {pname:4s}: {ms:9.4f} ms  {B / ms * 1e3:12.0f} qps  "
                   f"{gb / ms * 1e3:7.0f} GB/s/pass  {tf / ms * 1e3:8.1f} TFLOP/s")
     idx.close()
 

@@ -33,13 +33,21 @@ def bf16_query_scores(stored, scale, q, metric=bf.METRIC_COSINE):
     return bf.scores_fp32(stored, scale, qb)
 
 
+VARIANTS = ["1cta", "2cta"]
+
+
+def variant_path(native, variant):
+    return {"1cta": native.PATH_MMA_1CTA, "2cta": native.PATH_MMA_2CTA, "auto": native.PATH_MMA}[variant]
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
 @pytest.mark.parametrize("D,B,n", [(384, 3, 1000), (384, 128, 4096), (64, 1, 130), (128, 130, 777), (512, 17, 2049),
-                                   (100, 5, 500), (384, 260, 3000)])
-def test_full_score_matrix(native, D, B, n):
+                                   (100, 5, 500), (384, 260, 3000), (384, 513, 70000)])
+def test_full_score_matrix(native, D, B, n, variant):
     """Every score the tcgen05 pipeline produces (all tiles, all K blocks, tails) vs the oracle."""
     idx, stored, scale, rng = build(native, n, D, seed=D + B + n)
     q = rng.standard_normal((B, D)).astype(np.float32)
-    got = idx.debug_mma_scores(q)
+    got = idx.debug_mma_scores(q, path=variant_path(native, variant))
     want = bf16_query_scores(stored, scale, q)
     assert got.shape == want.shape
     assert np.isfinite(got).all()
@@ -48,14 +56,16 @@ def test_full_score_matrix(native, D, B, n):
     idx.close()
 
 
+@pytest.mark.parametrize("variant", VARIANTS)
 @pytest.mark.parametrize("D,B,k,n", [(384, 1, 10, 70001), (384, 16, 10, 70001), (384, 128, 10, 50000),
                                      (384, 129, 10, 50000), (384, 300, 5, 30000), (384, 64, 100, 20000),
                                      (384, 8, 128, 5000), (384, 5, 10, 7), (384, 5, 10, 128), (384, 5, 10, 129),
-                                     (64, 32, 1, 10000), (512, 40, 20, 10000), (200, 9, 10, 10000)])
-def test_mma_topk_parity(native, D, B, k, n):
+                                     (384, 5, 10, 257), (64, 32, 1, 10000), (512, 40, 20, 10000), (200, 9, 10, 10000),
+                                     (384, 600, 10, 200000), (384, 1024, 30, 60000)])
+def test_mma_topk_parity(native, D, B, k, n, variant):
     idx, stored, scale, rng = build(native, n, D, seed=D * 7 + B * 3 + k + n)
     q = rng.standard_normal((B, D)).astype(np.float32)
-    scores, rows, counts = idx.query(q, k, path=native.PATH_MMA)
+    scores, rows, counts = idx.query(q, k, path=variant_path(native, variant))
     assert idx.stats().last_path == native.PATH_MMA
     # exactness against what the tensor path computes ...
     check_topk(scores, rows, counts, bf16_query_scores(stored, scale, q), None, k, tol=3e-6)
@@ -75,7 +85,8 @@ def test_mma_and_scan_paths_agree(native):
     idx.close()
 
 
-def test_mma_ties_and_duplicates(native):
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_mma_ties_and_duplicates(native, variant):
     rng = np.random.default_rng(7)
     D, k = 384, 10
     base = rng.standard_normal((50, D)).astype(np.float32)
@@ -83,14 +94,15 @@ def test_mma_ties_and_duplicates(native):
     idx = native.NativeIndex(D)
     idx.upsert(x)
     q = np.repeat(base[3:4], 6, axis=0) + 0.0
-    scores, rows, counts = idx.query(q, k, path=native.PATH_MMA)
+    scores, rows, counts = idx.query(q, k, path=variant_path(native, variant))
     for b in range(6):
         assert rows[b].tolist() == [3 + 50 * i for i in range(k)]  # exact ties -> ascending row id
         assert len(set(scores[b].tolist())) == 1
     idx.close()
 
 
-def test_mma_predicates_and_row_offset(native):
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_mma_predicates_and_row_offset(native, variant):
     rng = np.random.default_rng(11)
     n, D, k, B = 30000, 384, 20, 7
     ns = rng.integers(0, 10, n).astype(np.uint32)
@@ -102,9 +114,9 @@ def test_mma_predicates_and_row_offset(native):
     words = np.packbits(np.concatenate([bits, np.zeros((-n) % 32, bool)]), bitorder="little").view(np.uint32)
     for kw, el in (({"ns_code": 3}, ns == 3), ({"ns_code": 3, "label_code": 1}, (ns == 3) & (label == 1)),
                    ({"mask": words}, bits), ({"mask": words, "ns_code": 5}, bits & (ns == 5))):
-        s, r, c = idx.query(q, k, path=native.PATH_MMA, **kw)
+        s, r, c = idx.query(q, k, path=variant_path(native, variant), **kw)
         check_topk(s, r, c, full, el, k, tol=3e-6, row_offset=5000)
-    s, r, c = idx.query(q, k, ns_code=77, path=native.PATH_MMA)
+    s, r, c = idx.query(q, k, ns_code=77, path=variant_path(native, variant))
     assert (c == 0).all() and (r == -1).all()
     idx.close()
 
