@@ -38,7 +38,7 @@ constexpr int kQ = 128;          // queries per tile  (UMMA M, TMEM lanes)
 constexpr int kTN = 128;         // corpus rows per tile (UMMA N, TMEM columns per accumulator stage)
 constexpr int kKB = 64;          // K elements per shared-memory block = 128 bytes = one swizzle row
 constexpr int kBlockBytes = kTN * kKB * 2;  // 16 KiB: one [128 rows][64] bf16 block (Q or corpus)
-constexpr int kStages = 6;       // corpus ring depth (96 KiB in flight per SM)
+constexpr int kMaxStages = 8;    // corpus ring depth: as many 16 KiB stages as fit next to the query tile (<= 8)
 constexpr int kAccStages = 2;
 constexpr int kThreads = 192;
 constexpr int kMaxKBlocks = 8;   // Dp <= 512 keeps the query tile resident next to the ring
@@ -56,6 +56,7 @@ struct KArgs {
     uint32_t ns_code, label_code;
     int64_t n;
     int kblocks;
+    int stages;     // ring depth actually used (<= kMaxStages)
     int k;
     uint32_t row_offset;
     int n_tiles;
@@ -310,13 +311,14 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
     // carve-up (all block bases 1024-byte aligned, as SWIZZLE_128B requires)
     unsigned char* sm_q = smem;                                           // kblocks x 16 KiB (own 128 queries)
     unsigned char* sm_ring = smem + static_cast<size_t>(a.kblocks) * kBlockBytes;  // kStages x 16 KiB (own 128 rows)
+    const int kStages = a.stages;
     float* sm_scale = reinterpret_cast<float*>(sm_ring + static_cast<size_t>(kStages) * kBlockBytes);  // [2][TN]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm_scale + kAccStages * TN);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1 + 2 * kAccStages);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1 + 2 * kAccStages);
 
-    const uint32_t bar_full = smem_u32(bars);                  // [kStages]   (leader's are the live ones)
-    const uint32_t bar_empty = bar_full + 8 * kStages;         // [kStages]
-    const uint32_t bar_q = bar_empty + 8 * kStages;            // [1]
+    const uint32_t bar_full = smem_u32(bars);                  // [kMaxStages] (leader's are the live ones)
+    const uint32_t bar_empty = bar_full + 8 * kMaxStages;      // [kMaxStages]
+    const uint32_t bar_q = bar_empty + 8 * kMaxStages;         // [1]
     const uint32_t bar_tfull = bar_q + 8;                      // [kAccStages]
     const uint32_t bar_tempty = bar_tfull + 8 * kAccStages;    // [kAccStages] (leader's are the live ones)
 
@@ -542,9 +544,17 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
     }
 }
 
-size_t mma_smem_bytes(int kblocks, int cg) {
-    return static_cast<size_t>(kblocks + kStages) * kBlockBytes + kAccStages * kTN * cg * sizeof(float) +
-           (2 * kStages + 1 + 2 * kAccStages) * sizeof(uint64_t) + 16;
+constexpr size_t kSmemLimit = 232448;  // 227 KiB: the per-CTA maximum on sm_100
+
+size_t mma_smem_bytes(int kblocks, int stages, int cg) {
+    return static_cast<size_t>(kblocks + stages) * kBlockBytes + kAccStages * kTN * cg * sizeof(float) +
+           (2 * kMaxStages + 1 + 2 * kAccStages) * sizeof(uint64_t) + 16;
+}
+
+int mma_stages(int kblocks, int cg) {
+    int s = kMaxStages;
+    while (s > 2 && mma_smem_bytes(kblocks, s, cg) > kSmemLimit) --s;
+    return s;
 }
 
 using MmaKernel = void (*)(const CUtensorMap, const CUtensorMap, const KArgs);
@@ -603,7 +613,8 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
     const int tile_rows = kTN * cg, tile_q = kQ * cg;
     const int n_tiles = static_cast<int>((m.n + tile_rows - 1) / tile_rows);
     const int units = m.sm_count / cg;  // CTAs or CTA pairs that fit the chip
-    const size_t smem = mma_smem_bytes(kblocks, cg);
+    const int stages = mma_stages(kblocks, cg);
+    const size_t smem = mma_smem_bytes(kblocks, stages, cg);
     MmaKernel kernel = cg == 2 ? pick_mma_kernel<2>(m.dump != nullptr, m.k) : pick_mma_kernel<1>(m.dump != nullptr, m.k);
     MMA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     // batches larger than one wave of query tiles are processed in slices
@@ -652,6 +663,7 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
         a.label_code = m.label_code;
         a.n = m.n;
         a.kblocks = kblocks;
+        a.stages = stages;
         a.k = m.k;
         a.row_offset = m.row_offset;
         a.n_tiles = n_tiles;
