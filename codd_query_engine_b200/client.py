@@ -23,6 +23,9 @@ library or a B200 is missing.
 
 from __future__ import annotations
 
+import json
+import os
+import re
 import threading
 import time
 import uuid
@@ -369,6 +372,64 @@ class Collection:
         if metadata is not None:
             self.metadata = dict(metadata)
 
+    # ------------------------------------------------------------------ persistence
+    # Snapshot = flat files: what the device holds (bf16 rows, scales, codes, read back through
+    # cv_get_rows) + one JSON line per row (id, metadata, document).  This replaces the Chroma
+    # server's docker volume (docker-compose.yml:8-9) -- SURVEY.md section 8(f) rank 3.
+    def save(self, directory: str) -> None:
+        with self._lock:
+            os.makedirs(directory, exist_ok=True)
+            n = len(self._ids)
+            meta = {"format": 1, "name": self.name, "metadata": self.metadata, "metric": self._metric,
+                    "label_field": self._label_field, "rows": n,
+                    "dim": None if self._index is None else self._index.dim,
+                    "ns_codes": list(self._ns_codes.items()), "label_codes": list(self._label_codes.items()),
+                    "free_rows": list(self._free_rows)}
+            if self._index is not None and n:
+                vec, scale, ns, lb = self._index.get_rows(np.arange(n, dtype=np.int64))
+                vec.tofile(os.path.join(directory, "rows.bf16"))
+                scale.tofile(os.path.join(directory, "scale.f32"))
+                ns.tofile(os.path.join(directory, "ns.u32"))
+                lb.tofile(os.path.join(directory, "label.u32"))
+            with open(os.path.join(directory, "records.jsonl"), "w", encoding="utf-8") as f:
+                for r in range(n):
+                    f.write(json.dumps({"id": self._ids[r], "metadata": self._metadatas[r], "document": self._documents[r]},
+                                       ensure_ascii=False) + "\n")
+            tmp = os.path.join(directory, "meta.json.tmp")
+            with open(tmp, "w", encoding="utf-8") as f:
+                json.dump(meta, f, ensure_ascii=False)
+            os.replace(tmp, os.path.join(directory, "meta.json"))  # meta.json last: its presence marks a complete snapshot
+
+    @classmethod
+    def load(cls, directory: str, embedding_function=None, device: int = 0) -> "Collection":
+        with open(os.path.join(directory, "meta.json"), encoding="utf-8") as f:
+            meta = json.load(f)
+        if meta.get("format") != 1:
+            raise ValueError(f"unknown snapshot format in {directory}")
+        coll = cls(meta["name"], meta["metadata"], embedding_function, device=device)
+        coll._label_field = meta["label_field"]
+        coll._ns_codes = {k: v for k, v in meta["ns_codes"]}
+        coll._label_codes = {k: v for k, v in meta["label_codes"]}
+        n, dim = int(meta["rows"]), meta["dim"]
+        with open(os.path.join(directory, "records.jsonl"), encoding="utf-8") as f:
+            for line in f:
+                rec = json.loads(line)
+                coll._ids.append(rec["id"])
+                coll._metadatas.append(rec["metadata"])
+                coll._documents.append(rec["document"])
+        if len(coll._ids) != n:
+            raise ValueError(f"snapshot {directory} is truncated: {len(coll._ids)} records for {n} rows")
+        coll._alive = np.array([i is not None for i in coll._ids], dtype=bool)
+        coll._row_of = {i: r for r, i in enumerate(coll._ids) if i is not None}
+        coll._free_rows = [int(r) for r in meta["free_rows"]]
+        if dim is not None and n:
+            vec = np.fromfile(os.path.join(directory, "rows.bf16"), dtype=np.uint16).reshape(n, dim)
+            scale = np.fromfile(os.path.join(directory, "scale.f32"), dtype=np.float32)
+            ns = np.fromfile(os.path.join(directory, "ns.u32"), dtype=np.uint32)
+            lb = np.fromfile(os.path.join(directory, "label.u32"), dtype=np.uint32)
+            coll._ensure_index(dim).load_rows(vec, scale, ns, lb)
+        return coll
+
     # ------------------------------------------------------------------ extras
     def stats(self):
         """Device-side counters (rows, launches, last query ms/bytes, path) -- SURVEY.md section 5."""
@@ -412,6 +473,38 @@ class Client:
         self._device = int(device)
         self._embedding_function = embedding_function
         self.endpoint = endpoint
+        self._path = endpoint[1] if isinstance(endpoint, tuple) and endpoint and endpoint[0] == "path" else None
+        if self._path is not None:
+            self._load_snapshots()
+
+    # ---- snapshots (PersistentClient): <path>/<collection>/{meta.json, rows.bf16, ...}
+    @staticmethod
+    def _dir_name(collection_name: str) -> str:
+        return re.sub(r"[^A-Za-z0-9._-]", "_", collection_name)
+
+    def _load_snapshots(self) -> None:
+        if not os.path.isdir(self._path):
+            return
+        with self._reg.lock:
+            for entry in sorted(os.listdir(self._path)):
+                d = os.path.join(self._path, entry)
+                if not os.path.isfile(os.path.join(d, "meta.json")):
+                    continue
+                with open(os.path.join(d, "meta.json"), encoding="utf-8") as f:
+                    name = json.load(f)["name"]
+                if name not in self._reg.collections:
+                    self._reg.collections[name] = Collection.load(d, self._embedding_function, device=self._device)
+
+    def persist(self, path: Optional[str] = None) -> str:
+        """Write every collection of this client to `path` (default: the PersistentClient path)."""
+        root = path or self._path
+        if root is None:
+            raise ValueError("persist() needs a path (or a client made with PersistentClient(path))")
+        with self._reg.lock:
+            colls = list(self._reg.collections.values())
+        for coll in colls:
+            coll.save(os.path.join(root, self._dir_name(coll.name)))
+        return root
 
     def heartbeat(self) -> int:
         """Nanosecond timestamp; raises if the CUDA library cannot be loaded (there is nothing to serve without it)."""
@@ -489,5 +582,8 @@ def HttpClient(host: str = "localhost", port: int = 8000, **kwargs) -> Client:  
 
 
 def PersistentClient(path: str = "./chroma", **kwargs) -> Client:  # noqa: N802
+    """Collections found under `path` are loaded onto the GPU; call ``client.persist()`` to write them
+    back (chromadb persists on every write; a flat-file snapshot of a device-resident corpus is an
+    explicit operation here)."""
     kwargs.pop("settings", None)
-    return Client(("path", str(path)), **kwargs)
+    return Client(("path", os.path.abspath(str(path))), **kwargs)

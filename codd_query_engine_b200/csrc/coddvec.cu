@@ -735,6 +735,33 @@ int cv_merge_keys_device(int32_t device, const uint64_t* d_keys_in, int32_t G, i
     return CV_OK;
 }
 
+int cv_load_rows(cv_index* idx, const uint16_t* bf16, const float* scale, const uint32_t* ns_codes,
+                 const uint32_t* label_codes, int64_t n, int64_t* out_rows) {
+    if (!idx || n < 0 || (n > 0 && (!bf16 || !scale))) return fail(CV_ERR_INVALID, "bad argument");
+    if (n == 0) return CV_OK;
+    DeviceGuard dg(idx->cfg.device);
+    if (!dg.ok) return fail(CV_ERR_CUDA, "cudaSetDevice(%d) failed", idx->cfg.device);
+    std::lock_guard<std::mutex> wg(idx->upsert_mu);
+    const int64_t base = idx->n_committed.load(std::memory_order_acquire);
+    int rc = ensure_capacity(idx, base + n);
+    if (rc) return rc;
+    cudaStream_t s = idx->upsert_stream;
+    const size_t pitch = static_cast<size_t>(idx->Dp) * 2;
+    if (idx->Dp != idx->D) CV_CUDA(cudaMemsetAsync(idx->E.ptr<unsigned char>() + base * pitch, 0, pitch * n, s));
+    CV_CUDA(cudaMemcpy2DAsync(idx->E.ptr<unsigned char>() + base * pitch, pitch, bf16, static_cast<size_t>(idx->D) * 2,
+                              static_cast<size_t>(idx->D) * 2, n, cudaMemcpyHostToDevice, s));
+    CV_CUDA(cudaMemcpyAsync(idx->scale.ptr<float>() + base, scale, sizeof(float) * n, cudaMemcpyHostToDevice, s));
+    if (ns_codes) CV_CUDA(cudaMemcpyAsync(idx->ns.ptr<uint32_t>() + base, ns_codes, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, s));
+    else CV_CUDA(cudaMemsetAsync(idx->ns.ptr<uint32_t>() + base, 0, sizeof(uint32_t) * n, s));
+    if (label_codes) CV_CUDA(cudaMemcpyAsync(idx->label.ptr<uint32_t>() + base, label_codes, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, s));
+    else CV_CUDA(cudaMemsetAsync(idx->label.ptr<uint32_t>() + base, 0, sizeof(uint32_t) * n, s));
+    CV_CUDA(cudaStreamSynchronize(s));
+    idx->n_committed.store(base + n, std::memory_order_release);
+    if (out_rows)
+        for (int64_t i = 0; i < n; ++i) out_rows[i] = base + i;
+    return CV_OK;
+}
+
 int cv_get_rows(cv_index* idx, const int64_t* rows, int64_t n, uint16_t* out_bf16, float* out_scale, uint32_t* out_ns,
                 uint32_t* out_label) {
     if (!idx || (!rows && n > 0)) return fail(CV_ERR_INVALID, "null argument");

@@ -118,6 +118,7 @@ def load_library() -> ctypes.CDLL:
         "cv_decode_keys": (None, [vp, i64, vp, vp]),
         "cv_encode_key": (u64, [ctypes.c_float, u32]),
         "cv_get_rows": (ctypes.c_int, [vp, vp, i64, vp, vp, vp, vp]),
+        "cv_load_rows": (ctypes.c_int, [vp, vp, vp, vp, vp, i64, vp]),
         "cv_debug_mma_scores": (ctypes.c_int, [vp, vp, i32, i32, vp]),
         "cv_count": (i64, [vp]),
         "cv_dim": (i32, [vp]),
@@ -137,7 +138,7 @@ def load_library() -> ctypes.CDLL:
 
 EXPORTED_SYMBOLS = (
     "cv_create", "cv_destroy", "cv_upsert", "cv_upsert_device", "cv_query", "cv_query_device",
-    "cv_merge_keys_device", "cv_decode_keys", "cv_encode_key", "cv_get_rows", "cv_debug_mma_scores", "cv_count", "cv_dim",
+    "cv_merge_keys_device", "cv_decode_keys", "cv_encode_key", "cv_get_rows", "cv_load_rows", "cv_debug_mma_scores", "cv_count", "cv_dim",
     "cv_set_profiling", "cv_stats", "cv_synchronize", "cv_last_error", "cv_version",
 )
 
@@ -242,6 +243,22 @@ class NativeIndex:
         r = None if rows is None else np.ascontiguousarray(rows, dtype=np.int64)
         out = np.empty(n, dtype=np.int64)
         _check(self._lib.cv_upsert_device(self._h, _ptr(r), emb_ptr, ns_ptr or None, label_ptr or None, n, _ptr(out)))
+        return out
+
+    def load_rows(self, stored_bf16: np.ndarray, scale: np.ndarray, ns_codes=None, label_codes=None) -> np.ndarray:
+        """Append rows exactly as get_rows returned them (snapshot restore; no re-normalisation)."""
+        vec = np.ascontiguousarray(stored_bf16, dtype=np.uint16)
+        if vec.ndim != 2 or vec.shape[1] != self.dim:
+            raise ValueError(f"stored rows must be [n][{self.dim}] uint16, got {vec.shape}")
+        n = vec.shape[0]
+        sc = np.ascontiguousarray(scale, dtype=np.float32)
+        ns = None if ns_codes is None else np.ascontiguousarray(ns_codes, dtype=np.uint32)
+        lb = None if label_codes is None else np.ascontiguousarray(label_codes, dtype=np.uint32)
+        for name, arr in (("scale", sc), ("ns_codes", ns), ("label_codes", lb)):
+            if arr is not None and arr.shape != (n,):
+                raise ValueError(f"{name} must have shape ({n},)")
+        out = np.empty(n, dtype=np.int64)
+        _check(self._lib.cv_load_rows(self._h, _ptr(vec), _ptr(sc), _ptr(ns), _ptr(lb), n, _ptr(out)))
         return out
 
     # -- K2 / K3 / K4

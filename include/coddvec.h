@@ -135,6 +135,12 @@ uint64_t cv_encode_key(float score, uint32_t global_row);
 int cv_get_rows(cv_index* idx, const int64_t* rows, int64_t n, uint16_t* out_bf16, float* out_scale,
                 uint32_t* out_ns, uint32_t* out_label);
 
+/* Append n rows verbatim -- bf16 bit patterns [n][dim], scale [n], codes [n] (NULL = 0), all host memory,
+ * exactly what cv_get_rows returned -- without re-normalising: restores a snapshot (the role Chroma's
+ * on-disk volume plays for the reference, docker-compose.yml:8-9).  out_rows as for cv_upsert. */
+int cv_load_rows(cv_index* idx, const uint16_t* bf16, const float* scale, const uint32_t* ns_codes,
+                 const uint32_t* label_codes, int64_t n, int64_t* out_rows);
+
 /* Testing aid: run the tensor-core path (K3) for B queries and return EVERY score it computed,
  * out_scores[B][count] (host), so that tests can compare the whole score matrix with the oracle.
  * path: CV_PATH_MMA, CV_PATH_MMA_1CTA or CV_PATH_MMA_2CTA. */

@@ -66,6 +66,14 @@ class OracleIndex:
         return bf.query(self._stored, self._scale, q, k, metric=self.metric, mask_words=mask, ns=self._ns,
                         ns_code=ns_code, label=self._label, label_code=label_code, row_offset=self.row_offset)
 
+    def load_rows(self, stored_bf16, scale, ns_codes=None, label_codes=None):
+        n, base = stored_bf16.shape[0], len(self)
+        self._stored = np.concatenate([self._stored, np.asarray(stored_bf16, np.uint16)])
+        self._scale = np.concatenate([self._scale, np.asarray(scale, np.float32)])
+        self._ns = np.concatenate([self._ns, np.zeros(n, np.uint32) if ns_codes is None else np.asarray(ns_codes, np.uint32)])
+        self._label = np.concatenate([self._label, np.zeros(n, np.uint32) if label_codes is None else np.asarray(label_codes, np.uint32)])
+        return np.arange(base, base + n, dtype=np.int64)
+
     def get_rows(self, rows, want_vectors=True):
         r = np.asarray(rows, np.int64)
         return self._stored[r], self._scale[r], self._ns[r], self._label[r]

@@ -201,6 +201,35 @@ def test_ip_space(client):
         client.get_or_create_collection("l2", metadata={"hnsw:space": "l2"})
 
 
+def test_snapshot_roundtrip(client, tmp_path, request, monkeypatch):
+    coll = client.get_or_create_collection("metrics semantic/1", metadata=COSINE)
+    x = vecs(200, d=100, seed=8)
+    coll.upsert(ids=[f"ns{i % 3}#m{i}" for i in range(200)], embeddings=x,
+                metadatas=[{"namespace": f"ns{i % 3}", "category": "c%d" % (i % 2), "i": i} for i in range(200)],
+                documents=[f"doc {i} \u00fc" for i in range(200)])
+    coll.delete(ids=["ns1#m1", "ns2#m2"])
+    q = vecs(2, d=100, seed=9)
+    before = coll.query(query_embeddings=q, n_results=7, where={"namespace": "ns0"})
+    before_all = coll.query(query_embeddings=q, n_results=7)
+    root = client.persist(str(tmp_path / "snap"))
+    assert sorted(p.name for p in (tmp_path / "snap").iterdir()) == ["metrics_semantic_1"]
+    # a new persistent client pointed at the directory sees the same collection and answers identically
+    c2 = client_mod.PersistentClient(root)
+    try:
+        restored = c2.get_collection("metrics semantic/1")
+        assert restored.count() == 198 and restored.metadata == COSINE
+        after = restored.query(query_embeddings=q, n_results=7, where={"namespace": "ns0"})
+        after_all = restored.query(query_embeddings=q, n_results=7)
+        assert after["ids"] == before["ids"] and after["distances"] == before["distances"]
+        assert after_all["ids"] == before_all["ids"] and after_all["metadatas"] == before_all["metadatas"]
+        assert restored.get(ids=["ns0#m3"])["documents"] == ["doc 3 \u00fc"]
+        assert restored.get(ids=["ns1#m1"])["ids"] == []
+        restored.upsert(ids=["fresh"], embeddings=q[:1])          # tombstoned slot is reused after restore
+        assert restored.count() == 199 and restored.query(query_embeddings=q[:1], n_results=1)["ids"] == [["fresh"]]
+    finally:
+        c2.reset()
+
+
 # ---------------------------------------------------------------- where compiler (pure host logic)
 def test_where_compiler_splits_fused_and_residual_predicates():
     mds = [{"namespace": "a", "category": "x", "n": 1}, {"namespace": "b", "category": "x", "n": 2},
