@@ -116,18 +116,22 @@ __device__ __forceinline__ void block_bitonic_desc(uint64_t* buf, int n) {
 // Strategy: append survivors to buf; whenever fewer than blockDim.x free slots remain, sort buf,
 // keep the best k, and raise tau to the k-th.
 // ---------------------------------------------------------------------------------------------
-constexpr int kSelCap = 2048;
+constexpr int kSelCap = 4096;
 
-template <typename Src>
+// U = candidates fetched per thread per round: the final cross-CTA merge reads its candidates from
+// L2, so all U loads of a round are issued before any is consumed (one L2 round trip per round
+// instead of one per candidate).  Requires blockDim.x * U <= kSelCap / 2.
+template <int U = 1, typename Src>
 __device__ __forceinline__ void block_select_topk(Src src, int m, int k, uint64_t tau, uint64_t* buf,
                                                   int* cnt) {
     __shared__ uint64_t s_tau;
     __syncthreads();  // buf / cnt may still be in use by the caller's previous phase
     if (threadIdx.x == 0) { *cnt = 0; s_tau = tau; }
     __syncthreads();
+    const int round = static_cast<int>(blockDim.x) * U;
     int c = 0;  // block-uniform running count (tracked with __syncthreads_count, no re-read races)
-    for (int base = 0; base < m; base += blockDim.x) {
-        if (c > kSelCap - static_cast<int>(blockDim.x)) {
+    for (int base = 0; base < m; base += round) {
+        if (c > kSelCap - round) {
             for (int i = c + threadIdx.x; i < kSelCap; i += blockDim.x) buf[i] = 0ull;
             block_bitonic_desc(buf, kSelCap);
             if (threadIdx.x == 0) {
@@ -140,14 +144,28 @@ __device__ __forceinline__ void block_select_topk(Src src, int m, int k, uint64_
             c = *cnt;
             __syncthreads();
         }
-        int i = base + threadIdx.x;
-        uint64_t key = (i < m) ? src(i) : 0ull;
-        const bool want = key != 0ull && key >= s_tau;
-        if (want) {
-            int p = atomicAdd(cnt, 1);
-            buf[p] = key;
+        uint64_t key[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = base + u * static_cast<int>(blockDim.x) + threadIdx.x;
+            key[u] = (i < m) ? src(i) : 0ull;
         }
-        c += __syncthreads_count(want);
+        int mine = 0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (key[u] != 0ull && key[u] >= s_tau) {
+                int p = atomicAdd(cnt, 1);
+                buf[p] = key[u];
+                ++mine;
+            }
+        }
+        if (U == 1) {
+            c += __syncthreads_count(mine);
+        } else {
+            __syncthreads();
+            c = *cnt;          // everyone reads the same value ...
+            __syncthreads();   // ... before anyone appends again
+        }
     }
     int n = 32;
     while (n < c || n < k) n <<= 1;  // c <= kSelCap, k <= kMaxK

@@ -132,7 +132,7 @@ __device__ __forceinline__ void publish_and_final_merge(const uint64_t* lists, i
         }
         tau = block_max_u64(tau, s_red);
         auto src = [&](int i) { return __ldcg(pb + i); };
-        block_select_topk(src, G * k, k, tau, selbuf, s_cnt);
+        block_select_topk<8>(src, G * k, k, tau, selbuf, s_cnt);
         for (int j = threadIdx.x; j < k; j += blockDim.x) out[static_cast<size_t>(b) * k + j] = selbuf[j];
         __syncthreads();
     }
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(kScanThreads, (NCH * QB <= 6) ? 2 : 1) k_scan_
     static_assert(V <= 16, "too many partial sums per half-warp");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t* selbuf = reinterpret_cast<uint64_t*>(smem_raw);                 // kSelCap keys (16 KB)
+    uint64_t* selbuf = reinterpret_cast<uint64_t*>(smem_raw);                 // kSelCap keys (32 KB)
     uint64_t* lists = selbuf + kSelCap;                                       // [warps][QB][k]
     float* sq = reinterpret_cast<float*>(smem_raw);                           // prologue alias: [QB][D]
     __shared__ float s_norm[QB];
@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(256) k_merge_keys(const uint64_t* in, int G, i
         tau = block_max_u64(tau, s_red);
     }
     auto src = [&](int i) { int g = i / k_in, j = i - g * k_in; return in[(static_cast<size_t>(g) * B + b) * k_in + j]; };
-    block_select_topk(src, G * k_in, k_out, tau, selbuf, &s_cnt);
+    block_select_topk<8>(src, G * k_in, k_out, tau, selbuf, &s_cnt);
     for (int j = threadIdx.x; j < k_out; j += blockDim.x) out[static_cast<size_t>(b) * k_out + j] = selbuf[j];
 }
 #endif  // CV_MAIN_TU
