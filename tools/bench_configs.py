@@ -125,8 +125,62 @@ def cfg5(rows):
             "k1_bit_exact": k1_exact, "final_query_parity_vs_oracle": parity}
 
 
+def cfg1(rows=10_000):
+    """BASELINE configs[0]: the repo's semantic store over 10k synthetic 384-d metric embeddings, one
+    query, top-10 -- through the chromadb-compatible Collection and the store facade (end to end, host
+    in / host out), beside the CPU oracle on the same vectors."""
+    from codd_query_engine_b200.client import Client
+    from codd_query_engine_b200.semantic_store import MetricsSemanticMetadataStore
+
+    D, k = 384, 10
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((rows, D), dtype=np.float32)
+    client = Client(endpoint="cfg1")
+    store = MetricsSemanticMetadataStore(client, collection_name="cfg1")
+    coll = store.collection
+    t0 = time.perf_counter()
+    for lo in range(0, rows, 1000):
+        coll.upsert(ids=[f"ns#metric.{i}" for i in range(lo, lo + 1000)], embeddings=x[lo:lo + 1000],
+                    metadatas=[{"namespace": "ns", "description": f"synthetic metric {i}"} for i in range(lo, lo + 1000)],
+                    documents=[f"synthetic metric {i}" for i in range(lo, lo + 1000)])
+    t_index = time.perf_counter() - t0
+    q = rng.standard_normal((1, D), dtype=np.float32)
+    for _ in range(20):
+        coll.query(query_embeddings=q, n_results=k)
+    lat = []
+    for _ in range(500):
+        a = time.perf_counter()
+        res = coll.query(query_embeddings=q, n_results=k)
+        lat.append(time.perf_counter() - a)
+    lat_text = []
+    for i in range(200):
+        a = time.perf_counter()
+        hits = store.search_metadata(f"synthetic metric {i * 37}", n_results=k)
+        lat_text.append(time.perf_counter() - a)
+    # CPU oracle on the same stored vectors (checker + baseline)
+    idx = coll._index
+    stored, scale, _, _ = idx.get_rows(np.arange(rows))
+    lib = bench.load_c_oracle()
+    bench.cpu_time_queries(lib, stored, scale, q, k, 5)
+    t_cpu, threads, okeys = bench.cpu_time_queries(lib, stored, scale, q, k, 200)
+    os_, or_ = bf.unpack_keys(okeys)
+    parity = [f"ns#metric.{r}" for r in or_[0]] == res["ids"][0] and bool(np.allclose(1 - os_[0], res["distances"][0], atol=2e-6))
+    top_text_ok = hits[0]["metric_name"] == f"metric.{199 * 37}"
+    client.reset()
+    lat, lat_text = np.array(lat) * 1e3, np.array(lat_text) * 1e3
+    return {"config": "cfg1", "workload": f"{rows} x 384 metric embeddings in the semantic store, 1 query, top-{k}",
+            "collection_query_ms_p50": float(np.percentile(lat, 50)), "collection_query_ms_p99": float(np.percentile(lat, 99)),
+            "collection_qps": float(1e3 / np.mean(lat)),
+            "store_search_metadata_ms_p50": float(np.percentile(lat_text, 50)),
+            "index_rows_per_s": rows / t_index,
+            "cpu_oracle_ms_per_query": float(np.median(t_cpu) * 1e3), "cpu_oracle_qps": float(1 / np.median(t_cpu)), "cpu_threads": threads,
+            "parity_vs_oracle": bool(parity), "text_query_top1_correct": bool(top_text_ok)}
+
+
 def main():
-    want = [a for a in sys.argv[1:] if a.startswith("cfg")] or ["cfg3", "cfg5"]
+    want = [a for a in sys.argv[1:] if a.startswith("cfg")] or ["cfg1", "cfg3", "cfg5"]
+    if "cfg1" in want:
+        print(json.dumps(cfg1()), flush=True)
     if "cfg3" in want:
         print(json.dumps(cfg3(arg("--rows3", 10_000_000))), flush=True)
     if "cfg5" in want:
