@@ -41,7 +41,7 @@ constexpr int kBlockBytes = kTN * kKB * 2;  // 16 KiB: one [128 rows][64] bf16 b
 constexpr int kMaxStages = 8;    // corpus ring depth: as many 16 KiB stages as fit next to the query tile (<= 8)
 constexpr int kAccStages = 2;
 constexpr int kThreads = 192;
-constexpr int kMaxKBlocks = 8;   // Dp <= 512 keeps the query tile resident next to the ring
+constexpr int kMaxKBlocks = 12;  // Dp <= 768: the query tile (<= 192 KiB) stays resident next to a >= 2-stage ring
 constexpr uint32_t kTmemCols = kAccStages * kTN;  // 256
 
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
@@ -64,6 +64,7 @@ struct KArgs {
     int P;          // CTAs sharing one query tile
     int Bpad;
     int B;            // real queries in this slice (lanes >= B are padding)
+    int smem_lists;   // k > 32: 1 = the per-query lists live in shared memory during the scan
     uint64_t* lists;  // [P][Bpad][k]
     uint32_t* gthr;   // [Bpad] shared per-query lower bounds on the k-th best score (ordered-float encoding)
     float* dump;      // debug: [Bpad][dump_ld] scores, or nullptr
@@ -315,6 +316,7 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
     float* sm_scale = reinterpret_cast<float*>(sm_ring + static_cast<size_t>(kStages) * kBlockBytes);  // [2][TN]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm_scale + kAccStages * TN);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1 + 2 * kAccStages);
+    uint64_t* sm_lists = reinterpret_cast<uint64_t*>(tmem_slot + 4);  // [128][k] when a.smem_lists
 
     const uint32_t bar_full = smem_u32(bars);                  // [kMaxStages] (leader's are the live ones)
     const uint32_t bar_empty = bar_full + 8 * kMaxStages;      // [kMaxStages]
@@ -405,7 +407,10 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
         const int et = threadIdx.x - 64;                 // 0..127
         const int qlane = 32 * (warp & 3) + lane;        // TMEM lane = query within this CTA's 128
         const int qglobal = (qt * CG + static_cast<int>(rank)) * kQ + qlane;
-        uint64_t* list = a.lists + (static_cast<size_t>(p) * a.Bpad + qglobal) * a.k;
+        uint64_t* const glist = a.lists + (static_cast<size_t>(p) * a.Bpad + qglobal) * a.k;
+        // large k (KREG == 0): the working list is in shared memory when it fits (fast warp-cooperative
+        // insertion), else directly in global memory; lanes of a warp own consecutive lists either way
+        uint64_t* list = (KREG == 0 && a.smem_lists) ? sm_lists + static_cast<size_t>(qlane) * a.k : glist;
         constexpr int KR = KREG > 0 ? KREG : 1;
         // k <= KREG: the list lives in registers, right-aligned -- slots [KREG-k, KREG) hold the top-k
         // descending, the slots before them are never-beaten sentinels -- so the k-th best is always
@@ -533,7 +538,10 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
         if (KREG > 0) {
 #pragma unroll
             for (int j = 0; j < KR; ++j)
-                if (j >= KR - a.k) list[j - (KR - a.k)] = L[j];
+                if (j >= KR - a.k) glist[j - (KR - a.k)] = L[j];
+        } else if (a.smem_lists) {
+            __syncwarp();
+            for (int j = 0; j < a.k; ++j) glist[j] = list[j];
         }
     }
     tc_fence_before();
@@ -546,14 +554,14 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
 
 constexpr size_t kSmemLimit = 232448;  // 227 KiB: the per-CTA maximum on sm_100
 
-size_t mma_smem_bytes(int kblocks, int stages, int cg) {
+size_t mma_smem_bytes(int kblocks, int stages, int cg, size_t list_bytes) {
     return static_cast<size_t>(kblocks + stages) * kBlockBytes + kAccStages * kTN * cg * sizeof(float) +
-           (2 * kMaxStages + 1 + 2 * kAccStages) * sizeof(uint64_t) + 16;
+           (2 * kMaxStages + 1 + 2 * kAccStages) * sizeof(uint64_t) + 16 + list_bytes;
 }
 
-int mma_stages(int kblocks, int cg) {
+int mma_stages(int kblocks, int cg, size_t list_bytes) {
     int s = kMaxStages;
-    while (s > 2 && mma_smem_bytes(kblocks, s, cg) > kSmemLimit) --s;
+    while (s > 2 && mma_smem_bytes(kblocks, s, cg, list_bytes) > kSmemLimit) --s;
     return s;
 }
 
@@ -605,7 +613,7 @@ std::string& mma_error() { return g_mma_err; }
 
 int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* launches) {
     if (!mma_supported(m.Dp))
-        return mma_fail(CV_ERR_UNSUPPORTED, "tensor-core path supports padded dim <= 512 (got " + std::to_string(m.Dp) + ")");
+        return mma_fail(CV_ERR_UNSUPPORTED, "tensor-core path supports padded dim <= 768 (got " + std::to_string(m.Dp) + ")");
     const int kblocks = m.Dp / kKB;
     // CTA pairs (cta_group::2, 256 queries x 256 rows per tile) once a batch fills more than one
     // 128-query tile; single CTAs below that (the scan is HBM-bound there and pairs would idle lanes).
@@ -613,8 +621,13 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
     const int tile_rows = kTN * cg, tile_q = kQ * cg;
     const int n_tiles = static_cast<int>((m.n + tile_rows - 1) / tile_rows);
     const int units = m.sm_count / cg;  // CTAs or CTA pairs that fit the chip
-    const int stages = mma_stages(kblocks, cg);
-    const size_t smem = mma_smem_bytes(kblocks, stages, cg);
+    // k > 32: per-query lists go to shared memory if a >= 3-stage ring still fits beside them
+    size_t smem_list_bytes = m.k > 32 && !m.dump ? static_cast<size_t>(kQ) * m.k * sizeof(uint64_t) : 0;
+    if (smem_list_bytes && mma_smem_bytes(kblocks, 3, cg, smem_list_bytes) > kSmemLimit) smem_list_bytes = 0;
+    const int stages = mma_stages(kblocks, cg, smem_list_bytes);
+    const size_t smem = mma_smem_bytes(kblocks, stages, cg, smem_list_bytes);
+    if (smem > kSmemLimit)
+        return mma_fail(CV_ERR_UNSUPPORTED, "tensor-core path: query tile does not fit shared memory at dim " + std::to_string(m.Dp));
     MmaKernel kernel = cg == 2 ? pick_mma_kernel<2>(m.dump != nullptr, m.k) : pick_mma_kernel<1>(m.dump != nullptr, m.k);
     MMA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     // batches larger than one wave of query tiles are processed in slices
@@ -671,6 +684,7 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
         a.P = P;
         a.Bpad = Bpad;
         a.B = Bs;
+        a.smem_lists = smem_list_bytes ? 1 : 0;
         a.lists = lists;
         a.gthr = gthr;
         a.dump = m.dump ? m.dump + static_cast<size_t>(done) * m.dump_ld : nullptr;

@@ -42,7 +42,7 @@ def variant_path(native, variant):
 
 @pytest.mark.parametrize("variant", VARIANTS)
 @pytest.mark.parametrize("D,B,n", [(384, 3, 1000), (384, 128, 4096), (64, 1, 130), (128, 130, 777), (512, 17, 2049),
-                                   (100, 5, 500), (384, 260, 3000), (384, 513, 70000)])
+                                   (100, 5, 500), (384, 260, 3000), (384, 513, 70000), (768, 33, 3000)])
 def test_full_score_matrix(native, D, B, n, variant):
     """Every score the tcgen05 pipeline produces (all tiles, all K blocks, tails) vs the oracle."""
     idx, stored, scale, rng = build(native, n, D, seed=D + B + n)
@@ -61,7 +61,9 @@ def test_full_score_matrix(native, D, B, n, variant):
                                      (384, 129, 10, 50000), (384, 300, 5, 30000), (384, 64, 100, 20000),
                                      (384, 8, 128, 5000), (384, 5, 10, 7), (384, 5, 10, 128), (384, 5, 10, 129),
                                      (384, 5, 10, 257), (64, 32, 1, 10000), (512, 40, 20, 10000), (200, 9, 10, 10000),
-                                     (384, 600, 10, 200000), (384, 1024, 30, 60000)])
+                                     (384, 600, 10, 200000), (384, 1024, 30, 60000),
+                                     (768, 20, 50, 30000), (768, 300, 10, 30000), (700, 7, 10, 5000),
+                                     (384, 40, 50, 40000), (384, 130, 100, 40000), (256, 16, 128, 20000)])
 def test_mma_topk_parity(native, D, B, k, n, variant):
     idx, stored, scale, rng = build(native, n, D, seed=D * 7 + B * 3 + k + n)
     q = rng.standard_normal((B, D)).astype(np.float32)
@@ -130,8 +132,8 @@ def test_mma_ip_metric(native):
 
 
 def test_mma_unsupported_dim_is_loud_and_auto_falls_to_scan(native):
-    idx, stored, scale, rng = build(native, 2000, 768, seed=14)
-    q = rng.standard_normal((8, 768)).astype(np.float32)
+    idx, stored, scale, rng = build(native, 2000, 1024, seed=14)
+    q = rng.standard_normal((8, 1024)).astype(np.float32)
     with pytest.raises(native.NativeError):
         idx.query(q, 5, path=native.PATH_MMA)
     s, r, c = idx.query(q, 5)  # AUTO
