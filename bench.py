@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=1, help="queries per step")
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--path", choices=["auto", "scan", "mma"], default="auto")
+    ap.add_argument("--exchange", choices=["auto", "fused", "nccl"], default="auto",
+                    help="multi-GPU top-k exchange: fused NVLink peer stores inside the kernels, or NCCL all-gather + K4")
     ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline and the configs sweep")
     ap.add_argument("--cpu-sample-rows", type=int, default=2_000_000)
     return ap.parse_args()
@@ -274,7 +276,7 @@ def run_ours(args):
     pk = peaks()
 
     t_build = time.perf_counter()
-    index = ShardedIndex(D, args.rows, device=device)
+    index = ShardedIndex(D, args.rows, device=device, exchange=args.exchange, max_queries=max(B, 1), max_k=max(k, 1))
     build_shard(index, index.lo, index.hi, D, torch, device)
     torch.cuda.synchronize()
     local_rows = len(index.local)
@@ -289,7 +291,7 @@ def run_ours(args):
         secs = time_steps(torch, dist, world, lambda: index.query_device(q_dev, k, path=path), args.steps, args.warmup)
     l0 = index.local.stats().kernel_launches
     index.query_device(q_dev, k, path=path)
-    per_step_launches = index.local.stats().kernel_launches - l0 + (1 if world > 1 else 0)  # + K4 merge
+    per_step_launches = index.local.stats().kernel_launches - l0 + (1 if world > 1 and index.exchange == "nccl" else 0)  # + K4
     launches = int(per_step_launches * args.steps)
     ms_per_step = secs / args.steps * 1e3
     value = B * args.steps / secs
@@ -355,6 +357,7 @@ def run_ours(args):
         "gpu_launches": launches,
         "clocks": clk.summary(),
         "build_seconds": t_build, "rows_per_gpu": local_rows,
+        "exchange": index.exchange if world > 1 else "none (1 GPU)",
     }
 
     if rank == 0 and world == 1 and not args.no_extras:

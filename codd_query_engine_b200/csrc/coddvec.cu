@@ -109,6 +109,7 @@ struct QueryCtx {
     DevBuf<float> d_q;
     DevBuf<uint64_t> d_partial;
     DevBuf<uint64_t> d_out;
+    DevBuf<uint64_t> d_local;  // this GPU's top-k before the fused cross-GPU exchange
     DevBuf<uint32_t> d_mask;
     cv::MmaScratch mma;  // K3 scratch (bf16 queries, per-CTA lists)
     unsigned int* d_counter = nullptr;
@@ -263,12 +264,24 @@ int plan_scan(cv_index* idx, QueryCtx* c, int qb, int k, bool pred, ScanLaunch* 
 
 // Enqueue one query batch on `stream`.  d_q: [B][D] fp32 device, d_out: [B][k] device keys.
 int enqueue_query(cv_index* idx, QueryCtx* c, cudaStream_t stream, const float* d_q, const cv_query_params* p,
-                  const uint32_t* d_mask, uint64_t* d_out, float* dump = nullptr, int64_t dump_ld = 0) {
+                  const uint32_t* d_mask, uint64_t* d_out, float* dump = nullptr, int64_t dump_ld = 0,
+                  const PeerExchange* px = nullptr, uint64_t seq = 0) {
     const int B = p->n_queries, k = p->k;
     const int64_t n = idx->n_committed.load(std::memory_order_acquire);
     const bool pred = d_mask != nullptr || p->ns_code != CV_ANY || p->label_code != CV_ANY;
+    const bool exchange = px != nullptr && px->world > 1;
     if (n == 0) {
-        CV_CUDA(cudaMemsetAsync(d_out, 0, sizeof(uint64_t) * B * k, stream));
+        if (!exchange) {
+            CV_CUDA(cudaMemsetAsync(d_out, 0, sizeof(uint64_t) * B * k, stream));
+            return CV_OK;
+        }
+        // an empty shard still has to take part in the exchange (it publishes empty lists)
+        int rc0 = c->d_local.reserve(static_cast<size_t>(B) * k);
+        if (rc0) return rc0;
+        CV_CUDA(cudaMemsetAsync(c->d_local.p, 0, sizeof(uint64_t) * B * k, stream));
+        k_exchange_merge<<<B, 256, 0, stream>>>(*px, seq, 0, c->d_local.p, k, d_out);
+        CV_CUDA(cudaGetLastError());
+        idx->launches.fetch_add(1);
         return CV_OK;
     }
     const int nch = (idx->C + 15) / 16;
@@ -306,7 +319,11 @@ int enqueue_query(cv_index* idx, QueryCtx* c, cudaStream_t stream, const float* 
         m.q = d_q;
         m.B = B;
         m.k = k;
-        m.out = d_out;
+        if (exchange) {
+            int rcl = c->d_local.reserve(static_cast<size_t>(B) * k);
+            if (rcl) return rcl;
+        }
+        m.out = exchange ? c->d_local.p : d_out;
         m.dump = dump;
         m.dump_ld = dump_ld;
         m.counter = c->d_counter;
@@ -314,6 +331,11 @@ int enqueue_query(cv_index* idx, QueryCtx* c, cudaStream_t stream, const float* 
         m.stream = stream;
         int rc = mma_enqueue(m, c->mma, &idx->launches);
         if (rc != 0) return fail(rc, "%s", mma_error().c_str());
+        if (exchange) {
+            k_exchange_merge<<<B, 256, 0, stream>>>(*px, seq, 0, c->d_local.p, k, d_out);
+            CV_CUDA(cudaGetLastError());
+            idx->launches.fetch_add(1);
+        }
         passes_bytes = n * (2ll * idx->Dp + 4) * ((B + 255) / 256);
     } else {
         if (max_qb == 0)
@@ -345,6 +367,9 @@ int enqueue_query(cv_index* idx, QueryCtx* c, cudaStream_t stream, const float* 
             a.partial = c->d_partial.p;
             a.counter = c->d_counter;
             a.out = d_out + static_cast<size_t>(done) * k;
+            if (exchange) a.px = *px; else a.px.world = 0;
+            a.seq = seq;
+            a.q_base = done;
             L.fn<<<L.grid, kScanThreads, L.smem, stream>>>(a);
             CV_CUDA(cudaGetLastError());
             idx->launches.fetch_add(1);
@@ -610,6 +635,48 @@ int cv_query_device(cv_index* idx, const float* d_q, const cv_query_params* p, u
     cudaError_t e = cudaStreamWaitEvent(s, c->busy, 0);
     if (e == cudaSuccess) {
         rc = enqueue_query(idx, c, s, d_q, p, p->mask, d_out_keys);
+        e = cudaEventRecord(c->busy, s);
+    }
+    release_ctx(idx, c);
+    if (e != cudaSuccess) return fail(CV_ERR_CUDA, "stream ordering failed: %s", cudaGetErrorString(e));
+    return rc;
+}
+
+int64_t cv_peer_exchange_bytes(int32_t world, int32_t max_queries, int32_t max_k) {
+    if (world < 1 || world > CV_MAX_PEERS || max_queries < 1 || max_k < 1 || max_k > CV_MAX_K) return -1;
+    const int64_t flags = static_cast<int64_t>(world) * max_queries;
+    const int64_t keys = 2ll * world * max_queries * max_k;
+    return (flags + keys) * static_cast<int64_t>(sizeof(uint64_t));
+}
+
+int cv_query_device_exchange(cv_index* idx, const float* d_q, const cv_query_params* p, const cv_peer_exchange* px,
+                             uint64_t seq, uint64_t* d_out_keys, void* stream) {
+    int rc = check_query_params(idx, d_q, p);
+    if (rc) return rc;
+    if (!d_out_keys || !px) return fail(CV_ERR_INVALID, "null argument");
+    if (px->world < 2 || px->world > CV_MAX_PEERS || px->rank < 0 || px->rank >= px->world)
+        return fail(CV_ERR_INVALID, "bad peer exchange: world=%d rank=%d", px->world, px->rank);
+    if (p->n_queries > px->max_queries || p->k > px->max_k)
+        return fail(CV_ERR_INVALID, "batch %d x k %d exceeds the exchange buffer capacity %d x %d", p->n_queries, p->k,
+                    px->max_queries, px->max_k);
+    if (seq == 0) return fail(CV_ERR_INVALID, "seq must start at 1");
+    PeerExchange dx;
+    dx.world = px->world;
+    dx.rank = px->rank;
+    dx.max_q = px->max_queries;
+    dx.max_k = px->max_k;
+    for (int g = 0; g < kMaxPeers; ++g) dx.base[g] = g < px->world ? reinterpret_cast<uint64_t*>(px->buffers[g]) : nullptr;
+    for (int g = 0; g < px->world; ++g)
+        if (!dx.base[g]) return fail(CV_ERR_INVALID, "peer buffer %d is null", g);
+    DeviceGuard dg(idx->cfg.device);
+    if (!dg.ok) return fail(CV_ERR_CUDA, "cudaSetDevice(%d) failed", idx->cfg.device);
+    std::shared_lock<std::shared_mutex> rd(idx->overwrite_mu);
+    QueryCtx* c = nullptr;
+    if ((rc = acquire_ctx(idx, &c))) return rc;
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+    cudaError_t e = cudaStreamWaitEvent(s, c->busy, 0);
+    if (e == cudaSuccess) {
+        rc = enqueue_query(idx, c, s, d_q, p, p->mask, d_out_keys, nullptr, 0, &dx, seq);
         e = cudaEventRecord(c->busy, s);
     }
     release_ctx(idx, c);

@@ -173,6 +173,77 @@ __device__ __forceinline__ void block_select_topk(Src src, int m, int k, uint64_
     for (int i = c + threadIdx.x; i < n; i += blockDim.x) buf[i] = 0ull;
     block_bitonic_desc(buf, n);
 }
+// ---------------------------------------------------------------------------------------------
+// Fused multi-GPU exchange (row-sharded search): instead of "scan kernel -> NCCL all-gather -> merge
+// kernel", the block that holds a query's final per-GPU top-k stores it straight into EVERY peer's
+// exchange buffer over NVLink (peer-mapped pointers), raises a per-(source rank, query) sequence flag
+// with a system-scope release, waits for the other ranks' flags, and merges the G lists that landed in
+// its own buffer.  One kernel per GPU per query batch; no collective launch on the critical path.
+//
+// Exchange buffer of one rank (device memory, zero-initialised, mapped into every peer):
+//     flags [G][max_q]              u64   flags[src][q]  = seq of the last batch src published for query q
+//     keys  [2][G][max_q][max_k]    u64   keys[seq & 1][src][q][0..k)
+// Two key slots suffice: a rank can only start batch s+1 after it has seen every peer's batch-s flag,
+// and a peer publishes batch s only after it finished merging batch s-1 (stream order).
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxPeers = 8;
+
+struct PeerExchange {
+    int world;       // 0 / 1 = no exchange
+    int rank;
+    int max_q;
+    int max_k;
+    uint64_t* base[kMaxPeers];
+};
+
+__device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(uint64_t* p, uint64_t v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_relaxed_sys(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Whole block.  local[0..k) (shared memory, this GPU's final top-k for global query index q) is published
+// to all ranks; on return buf[0..k) holds the merged top-k of all ranks.  local may alias buf.
+__device__ __forceinline__ void exchange_and_merge(const PeerExchange& px, uint64_t seq, int q, const uint64_t* local,
+                                                   int k, uint64_t* buf, int* cnt) {
+    const int G = px.world;
+    const size_t flag_words = static_cast<size_t>(G) * px.max_q;
+    const size_t slot_words = static_cast<size_t>(G) * px.max_q * px.max_k;
+    const size_t key_off = flag_words + (seq & 1ull) * slot_words + (static_cast<size_t>(px.rank) * px.max_q + q) * px.max_k;
+    // 1. peer stores of my k keys (coalesced 8-byte stores over NVLink; my own copy goes the same way)
+    for (int i = threadIdx.x; i < G * k; i += blockDim.x) {
+        const int g = i / k, j = i - g * k;
+        st_relaxed_sys(px.base[g] + key_off + j, local[j]);
+    }
+    __threadfence_system();
+    __syncthreads();
+    // 2. raise my flag on every rank, then wait for every rank's flag in my own buffer
+    if (static_cast<int>(threadIdx.x) < G)
+        st_release_sys(px.base[threadIdx.x] + static_cast<size_t>(px.rank) * px.max_q + q, seq);
+    if (static_cast<int>(threadIdx.x) < G) {
+        const uint64_t* f = px.base[px.rank] + static_cast<size_t>(threadIdx.x) * px.max_q + q;
+        while (ld_acquire_sys(f) < seq) {}
+    }
+    __syncthreads();
+    // 3. merge the G lists that landed here
+    const uint64_t* mine = px.base[px.rank] + flag_words + (seq & 1ull) * slot_words;
+    auto src = [&](int i) {
+        const int g = i / k, j = i - g * k;
+        return ld_relaxed_sys(mine + (static_cast<size_t>(g) * px.max_q + q) * px.max_k + j);
+    };
+    block_select_topk<1>(src, G * k, k, 0ull, buf, cnt);
+}
 #endif  // __CUDACC__
 
 }  // namespace cv

@@ -40,6 +40,9 @@ struct ScanArgs {
     uint64_t* partial;      // [QB][gridDim.x][k]
     unsigned int* counter;  // self-resetting "CTAs done" counter
     uint64_t* out;          // [QB][k] final keys (desc, 0 padded)
+    PeerExchange px;        // world > 1: the last CTA also exchanges + merges across GPUs (fused)
+    uint64_t seq;           // exchange sequence number of this batch
+    int q_base;             // global query index of this launch's query 0
 };
 
 // Transposing butterfly over the 16 lanes of a half-warp.  On return the lane holds the full sum of
@@ -104,7 +107,8 @@ template <int QBn>
 __device__ __forceinline__ void publish_and_final_merge(const uint64_t* lists, int nlists, int k,
                                                         uint64_t* partial, unsigned int* counter,
                                                         uint64_t* out, uint64_t* selbuf, int* s_cnt,
-                                                        uint64_t* s_red) {
+                                                        uint64_t* s_red, const PeerExchange& px, uint64_t seq,
+                                                        int q_base) {
     __shared__ int s_last;
     __syncthreads();
 #pragma unroll 1
@@ -133,6 +137,7 @@ __device__ __forceinline__ void publish_and_final_merge(const uint64_t* lists, i
         tau = block_max_u64(tau, s_red);
         auto src = [&](int i) { return __ldcg(pb + i); };
         block_select_topk<8>(src, G * k, k, tau, selbuf, s_cnt);
+        if (px.world > 1) exchange_and_merge(px, seq, q_base + b, selbuf, k, selbuf, s_cnt);  // fused NVLink exchange
         for (int j = threadIdx.x; j < k; j += blockDim.x) out[static_cast<size_t>(b) * k + j] = selbuf[j];
         __syncthreads();
     }
@@ -319,7 +324,8 @@ __global__ void __launch_bounds__(kScanThreads, (NCH * QB <= 6) ? 2 : 1) k_scan_
         }
     }
 
-    publish_and_final_merge<QB>(lists, kScanWarps, k, a.partial, a.counter, a.out, selbuf, &s_cnt, s_red);
+    publish_and_final_merge<QB>(lists, kScanWarps, k, a.partial, a.counter, a.out, selbuf, &s_cnt, s_red, a.px, a.seq,
+                                a.q_base);
 }
 
 using ScanFn = void (*)(ScanArgs);
@@ -356,6 +362,19 @@ __global__ void __launch_bounds__(256) k_merge_keys(const uint64_t* in, int G, i
     auto src = [&](int i) { int g = i / k_in, j = i - g * k_in; return in[(static_cast<size_t>(g) * B + b) * k_in + j]; };
     block_select_topk<8>(src, G * k_in, k_out, tau, selbuf, &s_cnt);
     for (int j = threadIdx.x; j < k_out; j += blockDim.x) out[static_cast<size_t>(b) * k_out + j] = selbuf[j];
+}
+
+// Batched path: K3 leaves this GPU's top-k per query in `local` [B][k]; one CTA per query does the
+// fused NVLink exchange + cross-GPU merge.
+__global__ void __launch_bounds__(256) k_exchange_merge(PeerExchange px, uint64_t seq, int q_base, const uint64_t* local,
+                                                        int k, uint64_t* out) {
+    __shared__ __align__(16) uint64_t selbuf[kSelCap];
+    __shared__ int s_cnt;
+    const int b = blockIdx.x;
+    for (int j = threadIdx.x; j < k; j += blockDim.x) selbuf[j] = local[static_cast<size_t>(b) * k + j];
+    __syncthreads();
+    exchange_and_merge(px, seq, q_base + b, selbuf, k, selbuf, &s_cnt);
+    for (int j = threadIdx.x; j < k; j += blockDim.x) out[static_cast<size_t>(b) * k + j] = selbuf[j];
 }
 #endif  // CV_MAIN_TU
 

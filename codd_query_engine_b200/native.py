@@ -70,6 +70,16 @@ class _QueryParams(ctypes.Structure):
     ]
 
 
+class _PeerExchange(ctypes.Structure):
+    _fields_ = [
+        ("world", ctypes.c_int32),
+        ("rank", ctypes.c_int32),
+        ("max_queries", ctypes.c_int32),
+        ("max_k", ctypes.c_int32),
+        ("buffers", ctypes.c_uint64 * 8),
+    ]
+
+
 class Stats(ctypes.Structure):
     _fields_ = [
         ("rows", ctypes.c_int64),
@@ -114,6 +124,9 @@ def load_library() -> ctypes.CDLL:
         "cv_upsert_device": (ctypes.c_int, [vp, vp, vp, vp, vp, i64, vp]),
         "cv_query": (ctypes.c_int, [vp, vp, ctypes.POINTER(_QueryParams), vp, vp, vp]),
         "cv_query_device": (ctypes.c_int, [vp, vp, ctypes.POINTER(_QueryParams), vp, vp]),
+        "cv_peer_exchange_bytes": (i64, [i32, i32, i32]),
+        "cv_query_device_exchange": (ctypes.c_int, [vp, vp, ctypes.POINTER(_QueryParams), ctypes.POINTER(_PeerExchange),
+                                                    u64, vp, vp]),
         "cv_merge_keys_device": (ctypes.c_int, [i32, vp, i32, i32, i32, i32, vp, vp]),
         "cv_decode_keys": (None, [vp, i64, vp, vp]),
         "cv_encode_key": (u64, [ctypes.c_float, u32]),
@@ -138,7 +151,8 @@ def load_library() -> ctypes.CDLL:
 
 EXPORTED_SYMBOLS = (
     "cv_create", "cv_destroy", "cv_upsert", "cv_upsert_device", "cv_query", "cv_query_device",
-    "cv_merge_keys_device", "cv_decode_keys", "cv_encode_key", "cv_get_rows", "cv_load_rows", "cv_debug_mma_scores", "cv_count", "cv_dim",
+    "cv_peer_exchange_bytes", "cv_query_device_exchange", "cv_merge_keys_device", "cv_decode_keys",
+    "cv_encode_key", "cv_get_rows", "cv_load_rows", "cv_debug_mma_scores", "cv_count", "cv_dim",
     "cv_set_profiling", "cv_stats", "cv_synchronize", "cv_last_error", "cv_version",
 )
 
@@ -170,6 +184,20 @@ def decode_keys(keys: np.ndarray):
 
 def encode_key(score: float, row: int) -> int:
     return int(load_library().cv_encode_key(float(score), int(row)))
+
+
+def peer_exchange_bytes(world: int, max_queries: int, max_k: int) -> int:
+    n = int(load_library().cv_peer_exchange_bytes(world, max_queries, max_k))
+    if n < 0:
+        raise ValueError("bad peer exchange shape")
+    return n
+
+
+def make_peer_exchange(world: int, rank: int, max_queries: int, max_k: int, buffer_ptrs) -> _PeerExchange:
+    px = _PeerExchange(int(world), int(rank), int(max_queries), int(max_k))
+    for g, ptr in enumerate(buffer_ptrs):
+        px.buffers[g] = int(ptr)
+    return px
 
 
 CUDA_STREAM_LEGACY = 1  # cudaStreamLegacy: the handle that names the default (NULL) stream explicitly
@@ -292,6 +320,15 @@ class NativeIndex:
         torch.cuda.current_stream().cuda_stream (0 = the default stream)."""
         p = _QueryParams(int(B), int(k), int(ns_code), int(label_code), mask_ptr or None, int(path), 0)
         _check(self._lib.cv_query_device(self._h, q_ptr, ctypes.byref(p), out_keys_ptr, _stream_arg(stream)))
+
+    def query_device_exchange(self, q_ptr: int, B: int, k: int, out_keys_ptr: int, px: _PeerExchange, seq: int,
+                              ns_code: int = ANY, label_code: int = ANY, path: int = PATH_AUTO, stream=None) -> None:
+        """Row-sharded search with the cross-GPU exchange fused into the kernels (no NCCL call): scan this
+        shard, store the per-GPU top-k into every peer's exchange buffer over NVLink, wait for the peers'
+        flags, merge.  `out_keys_ptr` receives the global top-k.  Every rank must call with the same seq."""
+        p = _QueryParams(int(B), int(k), int(ns_code), int(label_code), None, int(path), 0)
+        _check(self._lib.cv_query_device_exchange(self._h, q_ptr, ctypes.byref(p), ctypes.byref(px), int(seq),
+                                                  out_keys_ptr, _stream_arg(stream)))
 
     # -- readback / bookkeeping
     def get_rows(self, rows, want_vectors: bool = True):

@@ -35,7 +35,11 @@ class ShardedIndex:
     """SPMD handle: every rank constructs it and calls the same methods in the same order."""
 
     def __init__(self, dim: int, total_rows: int, metric: int = native.METRIC_COSINE,
-                 group: Optional[dist.ProcessGroup] = None, device: Optional[torch.device] = None):
+                 group: Optional[dist.ProcessGroup] = None, device: Optional[torch.device] = None,
+                 exchange: str = "auto", max_queries: int = 1024, max_k: int = 32):
+        """exchange: "fused" = the kernels exchange per-GPU top-k themselves with NVLink peer stores into
+        symmetric buffers (no collective call per query); "nccl" = all-gather + K4 merge; "auto" = fused when
+        torch symmetric memory can map the peers, else nccl."""
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -48,6 +52,37 @@ class ShardedIndex:
                                  max_rows=max(self.hi - self.lo, 1), row_offset=self.lo)
         self._bufs: dict[tuple[int, int], tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = {}
         self._host: dict[tuple[int, int], tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = {}
+        self._px = None
+        self._seq = 0
+        self.exchange = "nccl"
+        if self.world > 1 and exchange in ("auto", "fused") and self.device.type == "cuda":
+            try:
+                self._setup_fused_exchange(int(max_queries), int(max_k))
+                self.exchange = "fused"
+            except Exception as exc:  # symmetric memory unavailable (no P2P / IPC): keep the NCCL path
+                if exchange == "fused":
+                    raise
+                self._px = None
+                self._exchange_error = repr(exc)
+            # every rank must take the same path
+            ok = torch.tensor([1 if self._px is not None else 0], device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if int(ok.item()) == 0:
+                self._px, self.exchange = None, "nccl"
+
+    def _setup_fused_exchange(self, max_queries: int, max_k: int) -> None:
+        import torch.distributed._symmetric_memory as symm_mem
+
+        nbytes = native.peer_exchange_bytes(self.world, max_queries, max_k)
+        group = self.group if self.group is not None else dist.group.WORLD
+        buf = symm_mem.empty(nbytes // 8, dtype=torch.int64, device=self.device)
+        buf.zero_()
+        handle = symm_mem.rendezvous(buf, group=group)
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)  # every rank's buffer is zeroed before anyone publishes into it
+        self._xbuf, self._xhandle = buf, handle
+        self._px = native.make_peer_exchange(self.world, self.rank, max_queries, max_k, list(handle.buffer_ptrs))
+        self._px_caps = (max_queries, max_k)
 
     # ------------------------------------------------------------------ loading
     def owns(self, global_row: int) -> bool:
@@ -88,6 +123,11 @@ class ShardedIndex:
         B = q.shape[0]
         local, gathered, merged = self._buffers(B, k)
         stream = self._stream()
+        if self.world > 1 and self._px is not None and B <= self._px_caps[0] and k <= self._px_caps[1]:
+            self._seq += 1  # fused: scan + NVLink peer stores + flag wait + merge, no collective launch
+            self.local.query_device_exchange(q.data_ptr(), B, k, merged.data_ptr(), self._px, self._seq, ns_code=ns_code,
+                                             label_code=label_code, path=path, stream=stream)
+            return merged
         self.local.query_device(q.data_ptr(), B, k, local.data_ptr(), ns_code=ns_code, label_code=label_code,
                                 path=path, stream=stream)
         if self.world == 1:

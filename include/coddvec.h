@@ -120,6 +120,24 @@ int cv_query(cv_index* idx, const float* q, const cv_query_params* p, float* out
 int cv_query_device(cv_index* idx, const float* d_q, const cv_query_params* p, uint64_t* d_out_keys,
                     void* stream);
 
+/* Fused multi-GPU search (row-sharded corpus, one process per GPU).  Every rank owns an exchange buffer of
+ * cv_peer_exchange_bytes() zero-initialised device bytes that is mapped into all peers (CUDA IPC / torch
+ * symmetric memory); `buffers[g]` is rank g's buffer as addressable from THIS process.  The kernel that
+ * finishes a query's per-GPU top-k stores it into every peer's buffer over NVLink, raises a sequence flag,
+ * waits for the peers' flags and merges -- no collective launch.  All ranks must issue the same batches in
+ * the same order with the same `seq` (1, 2, 3, ...).  d_out_keys receives the merged global top-k. */
+#define CV_MAX_PEERS 8
+typedef struct cv_peer_exchange {
+    int32_t world;       /* number of ranks, 2..CV_MAX_PEERS */
+    int32_t rank;        /* this rank */
+    int32_t max_queries; /* capacity: queries per batch */
+    int32_t max_k;       /* capacity: k */
+    uint64_t buffers[CV_MAX_PEERS]; /* device addresses */
+} cv_peer_exchange;
+int64_t cv_peer_exchange_bytes(int32_t world, int32_t max_queries, int32_t max_k);
+int cv_query_device_exchange(cv_index* idx, const float* d_q, const cv_query_params* p, const cv_peer_exchange* px,
+                             uint64_t seq, uint64_t* d_out_keys, void* stream);
+
 /* K4: merge G per-shard key lists [G][B][k_in] (device) into [B][k_out] (device) on `stream`
  * of `device`.  Used after the NCCL all-gather of per-GPU top-k. */
 int cv_merge_keys_device(int32_t device, const uint64_t* d_keys_in, int32_t G, int32_t B, int32_t k_in,

@@ -28,13 +28,31 @@ def main():
     x = rng.standard_normal((n, D)).astype(np.float32)
     x[n - 7] = x[11]  # cross-shard exact tie
     ns = rng.integers(1, 6, n).astype(np.uint32)
-    idx = ShardedIndex(D, n, device=dev)
-    idx.append_local(x[idx.lo:idx.hi], ns_codes=ns[idx.lo:idx.hi])
-    assert idx.count() == n
     whole = native.NativeIndex(D, device=local)
     whole.upsert(x, ns_codes=ns)
     ok = True
-    for B, path in ((1, native.PATH_SCAN), (3, native.PATH_SCAN), (64, native.PATH_MMA)):
+    modes = [m for m in os.environ.get("EXCHANGE_MODES", "nccl,fused").split(",") if m]
+    for mode in modes:
+        ok &= check_mode(mode, rank, world, dev, x, ns, n, D, k, whole, rng)
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("MULTI_GPU_CHECK", "OK" if int(flag.item()) == 1 else "FAILED")
+    whole.close()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+def check_mode(mode, rank, world, dev, x, ns, n, D, k, whole, rng):
+    idx = ShardedIndex(D, n, device=dev, exchange=mode, max_queries=256, max_k=32)
+    idx.append_local(x[idx.lo:idx.hi], ns_codes=ns[idx.lo:idx.hi])
+    assert idx.count() == n
+    if rank == 0:
+        print(f"exchange requested={mode} active={idx.exchange}")
+    ok = idx.exchange == mode
+    rng = np.random.default_rng(1)
+    for B, path in ((1, native.PATH_SCAN), (3, native.PATH_SCAN), (7, native.PATH_SCAN), (64, native.PATH_MMA),
+                    (200, native.PATH_MMA)):
         q = np.concatenate([x[11:12], rng.standard_normal((B - 1, D)).astype(np.float32)]) if B > 1 else x[11:12].copy()
         s, r, c = idx.query(q, k, path=path)
         ws, wr, wc = whole.query(q, k, path=path)
@@ -42,21 +60,21 @@ def main():
         tie = r[0, 0] == 11 and r[0, 1] == n - 7
         ok &= same and tie
         if rank == 0:
-            print(f"world={world} B={B} path={path}: identical_to_1gpu={same} tie_by_global_row={tie}")
+            print(f"world={world} {mode} B={B} path={path}: identical_to_1gpu={same} tie_by_global_row={tie}")
         s, r, c = idx.query(q, k, path=path, ns_code=3)
         ws, wr, wc = whole.query(q, k, path=path, ns_code=3)
         same = np.array_equal(r, wr) and np.array_equal(s, ws)
         ok &= same
         if rank == 0:
-            print(f"world={world} B={B} path={path} ns=3: identical_to_1gpu={same}")
-    flag = torch.tensor([1 if ok else 0], device=dev)
-    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    if rank == 0:
-        print("MULTI_GPU_CHECK", "OK" if int(flag.item()) == 1 else "FAILED")
+            print(f"world={world} {mode} B={B} path={path} ns=3: identical_to_1gpu={same}")
+    # repeated batches exercise the two key slots / sequence flags of the fused exchange
+    q = rng.standard_normal((2, D)).astype(np.float32)
+    ws, wr, wc = whole.query(q, k, path=native.PATH_SCAN)
+    for _ in range(50):
+        s, r, c = idx.query(q, k, path=native.PATH_SCAN)
+        ok &= bool(np.array_equal(r, wr) and np.array_equal(s, ws))
     idx.close()
-    whole.close()
-    dist.destroy_process_group()
-    sys.exit(0 if int(flag.item()) == 1 else 1)
+    return ok
 
 
 if __name__ == "__main__":
