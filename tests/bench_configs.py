@@ -1,12 +1,13 @@
 #!/usr/bin/env python
-"""Secondary BASELINE.json configs on one B200 (bench.py covers configs[1] and the 100M corpus):
+"""Parity-checked measurement of the secondary BASELINE.json configs on one B200 (lives under tests/ because
+it uses the oracle as its checker) (bench.py covers configs[1] and the 100M corpus):
 
   cfg3  10M x 768 bf16, fused namespace predicate at 10 % selectivity, top-50, batch 1 (K2 PRED)
   cfg5  bulk upsert of 1M x 384 fp32 host embeddings in chunks of 1000 (MAX_BULK_OPERATIONS,
         codd_dal/metrics/metrics_semantic_metadata_store.py:23) interleaved with live top-10 queries
 
 Each result is parity-checked against the oracle (checker only) and printed as one JSON line.
-    python tools/bench_configs.py [cfg3] [cfg5] [--rows3 N] [--rows5 N]
+    python tests/bench_configs.py [cfg3] [cfg5] [--rows3 N] [--rows5 N]
 """
 import json
 import os
