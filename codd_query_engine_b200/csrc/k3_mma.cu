@@ -264,22 +264,16 @@ __device__ __forceinline__ uint32_t pick32(const uint32_t (&v)[32], int j) {
     return (j & 16) ? d[1] : d[0];
 }
 
-// TMEM lane (= row of the query tile) <-> query index within a 128-query tile
-__host__ __device__ __forceinline__ int lane_to_query(int lane) { return (lane & 31) * 4 + (lane >> 5); }
-
 // ------------------------------------------------------------------------------------------ query prep
 // Normalise fp32 queries exactly like the oracle (fp64 norm, fp32 divide), round to bf16, zero-pad to
 // [Bpad][Dp].  One warp per query row.
 __global__ void __launch_bounds__(128) k_prep_queries(const float* q, int B, int Bpad, int D, int Dp, int cosine,
                                                       __nv_bfloat16* out, uint32_t* gthr) {
     const int lane = threadIdx.x & 31;
-    const int dst = blockIdx.x * 4 + (threadIdx.x >> 5);  // row of the bf16 query matrix = TMEM lane
-    if (dst >= Bpad) return;
-    if (lane == 0) gthr[dst] = 0u;
-    // Query b of a 128-query tile sits on TMEM lane (b % 4) * 32 + b / 4, so that a partial tile spreads
-    // its live queries over all four epilogue warps instead of filling warp 0 first.
-    const int row = (dst & ~127) + lane_to_query(dst & 127);
-    __nv_bfloat16* o = out + static_cast<size_t>(dst) * Dp;
+    const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (row >= Bpad) return;
+    if (lane == 0) gthr[row] = 0u;
+    __nv_bfloat16* o = out + static_cast<size_t>(row) * Dp;
     if (row >= B) {
         for (int d = lane; d < Dp; d += 32) o[d] = __float2bfloat16_rn(0.0f);
         return;
@@ -412,12 +406,11 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
         // ===================================================================== epilogue (128 threads per CTA)
         const int et = threadIdx.x - 64;                 // 0..127
         const int qlane = 32 * (warp & 3) + lane;        // TMEM lane = query within this CTA's 128
-        const int qglobal = (qt * CG + static_cast<int>(rank)) * kQ + lane_to_query(qlane);
+        const int qglobal = (qt * CG + static_cast<int>(rank)) * kQ + qlane;
         uint64_t* const glist = a.lists + (static_cast<size_t>(p) * a.Bpad + qglobal) * a.k;
         // large k (KREG == 0): the working list is in shared memory when it fits (fast warp-cooperative
         // insertion), else directly in global memory; lanes of a warp own consecutive lists either way
         uint64_t* list = (KREG == 0 && a.smem_lists) ? sm_lists + static_cast<size_t>(qlane) * a.k : glist;
-        const ptrdiff_t list_stride = (KREG == 0 && a.smem_lists) ? a.k : 4 * a.k;  // between neighbouring lanes' lists
         constexpr int KR = KREG > 0 ? KREG : 1;
         // k <= KREG: the list lives in registers, right-aligned -- slots [KREG-k, KREG) hold the top-k
         // descending, the slots before them are never-beaten sentinels -- so the k-th best is always
@@ -513,7 +506,7 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
                         uint32_t cm = __shfl_sync(kFullMask, cand, src);
                         float thr_src = __shfl_sync(kFullMask, thr, src);
                         float local_src = __shfl_sync(kFullMask, thr_local, src);
-                        uint64_t* lst = list + static_cast<ptrdiff_t>(src - lane) * list_stride;  // src lane's list
+                        uint64_t* lst = list + static_cast<ptrdiff_t>(src - lane) * a.k;  // src lane's list
                         bool changed = false;
                         while (cm) {
                             const int j = __ffs(cm) - 1;
