@@ -430,24 +430,34 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
         const bool pred = a.mask != nullptr || a.ns_code != kAny || a.label_code != kAny;
         int as = 0;
         uint32_t aphase = 0;
-        for (int t = p; t < a.n_tiles; t += a.P) {
-            // stage scale * eligibility for this tile's TN rows (NaN = skip)
-#pragma unroll
-            for (int h = 0; h < CG; ++h) {
-                const int64_t row = static_cast<int64_t>(t) * TN + h * kTN + et;
-                float sc = __int_as_float(0x7FC00000);
-                if (row < a.n) {
-                    bool ok = true;
-                    if (pred) {
-                        if (a.ns_code != kAny) ok = __ldg(a.ns + row) == a.ns_code;
-                        if (ok && a.label_code != kAny) ok = __ldg(a.label + row) == a.label_code;
-                        if (ok && a.mask) ok = (__ldg(a.mask + (row >> 5)) >> (row & 31)) & 1u;
-                    }
-                    if (ok) sc = __ldg(a.scale + row);
+        // scale * eligibility of one tile row (NaN = skip); loaded one tile ahead so that the L2/HBM latency
+        // of these small loads is never on the epilogue's critical path
+        auto row_scale = [&](int t, int h) -> float {
+            const int64_t row = static_cast<int64_t>(t) * TN + h * kTN + et;
+            float sc = __int_as_float(0x7FC00000);
+            if (t < a.n_tiles && row < a.n) {
+                bool ok = true;
+                if (pred) {
+                    if (a.ns_code != kAny) ok = __ldg(a.ns + row) == a.ns_code;
+                    if (ok && a.label_code != kAny) ok = __ldg(a.label + row) == a.label_code;
+                    if (ok && a.mask) ok = (__ldg(a.mask + (row >> 5)) >> (row & 31)) & 1u;
                 }
-                sm_scale[as * TN + h * kTN + et] = sc;
+                if (ok) sc = __ldg(a.scale + row);
             }
-            if (share) thr = fmaxf(thr_local, shared_threshold(__ldcg(a.gthr + qglobal)));
+            return sc;
+        };
+        float sc_next[CG];
+#pragma unroll
+        for (int h = 0; h < CG; ++h) sc_next[h] = row_scale(p, h);
+        uint32_t g_next = share ? __ldcg(a.gthr + qglobal) : 0u;
+        for (int t = p; t < a.n_tiles; t += a.P) {
+#pragma unroll
+            for (int h = 0; h < CG; ++h) sm_scale[as * TN + h * kTN + et] = sc_next[h];
+            if (share) thr = fmaxf(thr_local, shared_threshold(g_next));
+            // prefetch for the next tile of this CTA (in flight while this tile is processed)
+#pragma unroll
+            for (int h = 0; h < CG; ++h) sc_next[h] = row_scale(t + a.P, h);
+            if (share) g_next = __ldcg(a.gthr + qglobal);
             asm volatile("bar.sync 1, 128;" ::: "memory");  // this CTA's epilogue warps only
             mbar_wait(bar_tfull + 8 * as, aphase);
             tc_fence_after();
