@@ -283,25 +283,35 @@ __global__ void __launch_bounds__(kScanThreads, (NCH * QB <= 6) ? 2 : 1) k_scan_
             process(rows);
         }
     } else {
-        // 128 rows per warp step: build the eligibility words, then consume set bits S at a time.
+        // 128 rows per warp step: build the eligibility words, then consume set bits S at a time.  The
+        // codes / mask words of the NEXT step are loaded before the current step's rows are processed, so
+        // their latency overlaps the row loads instead of preceding them.
         const int64_t blocks = (a.n + 127) / 128;
         const int64_t nwords = (a.n + 31) / 32;
+        const bool use_ns = a.ns_code != kAny, use_label = a.label_code != kAny;
+        uint32_t nsv[4], lbv[4], mkv[4];
+        auto fetch = [&](int64_t blk) {
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const int64_t r = blk * 128 + 32 * w + lane;
+                const bool in = blk < blocks && r < a.n;
+                nsv[w] = (in && use_ns) ? __ldg(a.ns + r) : a.ns_code;
+                lbv[w] = (in && use_label) ? __ldg(a.label + r) : a.label_code;
+                const int64_t wi = blk * 4 + w;
+                mkv[w] = (a.mask && blk < blocks && wi < nwords) ? __ldg(a.mask + wi) : (a.mask ? 0u : 0xFFFFFFFFu);
+            }
+        };
+        fetch(gw);
         for (int64_t blk = gw; blk < blocks; blk += nw) {
             const int64_t base = blk * 128;
             uint32_t words[4];
 #pragma unroll
             for (int w = 0; w < 4; ++w) {
                 const int64_t r = base + 32 * w + lane;
-                bool ok = r < a.n;
-                if (ok && a.ns_code != kAny) ok = __ldg(a.ns + r) == a.ns_code;
-                if (ok && a.label_code != kAny) ok = __ldg(a.label + r) == a.label_code;
-                uint32_t word = __ballot_sync(kFullMask, ok);
-                if (a.mask) {
-                    const int64_t wi = (base >> 5) + w;
-                    word &= (wi < nwords) ? __ldg(a.mask + wi) : 0u;
-                }
-                words[w] = word;
+                const bool ok = r < a.n && nsv[w] == a.ns_code && lbv[w] == a.label_code;
+                words[w] = __ballot_sync(kFullMask, ok) & mkv[w];
             }
+            fetch(blk + nw);
             int remaining = __popc(words[0]) + __popc(words[1]) + __popc(words[2]) + __popc(words[3]);
             while (remaining > 0) {
                 int64_t rows[S];

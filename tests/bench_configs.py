@@ -43,7 +43,7 @@ def time_device(fn, iters, warm=5):
 
 
 def cfg3(rows):
-    D, k, sel_ns = 768, 50, 7
+    D, k, sel_ns = 768, arg("--k3", 50), 7
     pk = bench.peaks()
     idx = native.NativeIndex(D, capacity_rows=rows, max_rows=rows)
     gen = torch.Generator(device="cuda").manual_seed(2)
