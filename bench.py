@@ -402,7 +402,7 @@ def sweep_small_configs(torch, native, D, k, pk):
         idx.upsert_device(x.data_ptr(), rows)
         del x
         stream = torch.cuda.current_stream().cuda_stream
-        for B in (1, 4, 16, 64, 256):
+        for B in (1, 4, 16, 64, 256, 1024):
             q = torch.randn((B, D), device="cuda", generator=gen)
             keys = torch.zeros((B, k), dtype=torch.int64, device="cuda")
             fn = lambda: idx.query_device(q.data_ptr(), B, k, keys.data_ptr(), stream=stream)  # noqa: E731
