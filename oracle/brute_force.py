@@ -68,6 +68,10 @@ def bf16_bits_to_f32(b: np.ndarray) -> np.ndarray:
 def normalise_store(x: np.ndarray, metric: int = METRIC_COSINE):
     """fp32 [n][D] -> (stored bf16 bits uint16 [n][D], scale fp32 [n]).
 
+    Restates what `collection.upsert` does to a vector in cosine space
+    (codd_dal/metrics/metrics_semantic_metadata_store.py:236-238 with `hnsw:space=cosine`, :64;
+    hnswlib normalises at insert).
+
     cosine: stored = bf16(x / ||x||), scale = 1/||stored||  (0 for an all-zero row)
     ip:     stored = bf16(x),         scale = 1
     """
@@ -90,7 +94,10 @@ def normalise_store(x: np.ndarray, metric: int = METRIC_COSINE):
 
 
 def normalise_query(q: np.ndarray, metric: int = METRIC_COSINE) -> np.ndarray:
-    """fp32 [B][D] -> qhat fp32 [B][D] (cosine: q/||q||, zero query stays zero; ip: q)."""
+    """fp32 [B][D] -> qhat fp32 [B][D] (cosine: q/||q||, zero query stays zero; ip: q).
+
+    Query-side half of `collection.query` (codd_dal/metrics/metrics_semantic_metadata_store.py:314-316;
+    hnswlib cosine space normalises the query as well)."""
     q = np.ascontiguousarray(q, dtype=np.float32)
     if q.ndim == 1:
         q = q[None, :]
@@ -149,14 +156,19 @@ def eligible_rows(n, mask_words=None, ns=None, ns_code=ANY_CODE, label=None, lab
 
 
 def scores_fp32(stored_bits: np.ndarray, scale: np.ndarray, qhat: np.ndarray) -> np.ndarray:
-    """[B][n] fp32 scores = (stored @ qhat^T) * scale, fp32 accumulate."""
+    """[B][n] fp32 scores = (stored @ qhat^T) * scale, fp32 accumulate.
+
+    score = 1 - distance of codd_dal/metrics/metrics_semantic_metadata_store.py:336 (`similarity_score`)."""
     e = bf16_bits_to_f32(stored_bits)
     s = (e @ np.ascontiguousarray(qhat, dtype=np.float32).T).T  # [B][n]
     return (s * np.asarray(scale, dtype=np.float32)[None, :]).astype(np.float32)
 
 
 def topk_from_scores(scores: np.ndarray, k: int, eligible=None, row_offset: int = 0):
-    """Per query: k best keys (desc).  Returns keys u64 [B][k], EMPTY_KEY padded."""
+    """Per query: k best keys (desc).  Returns keys u64 [B][k], EMPTY_KEY padded.
+
+    `n_results` semantics of codd_dal/metrics/metrics_semantic_metadata_store.py:314-316: ascending distance,
+    fewer rows than asked -> what exists; ties (unspecified upstream) are broken by row id here."""
     scores = np.atleast_2d(scores)
     B, n = scores.shape
     out = np.zeros((B, k), dtype=np.uint64)
