@@ -44,6 +44,8 @@ constexpr int kThreads = 192;
 constexpr int kMaxKBlocks = 12;  // Dp <= 768: the query tile (<= 192 KiB) stays resident next to a >= 2-stage ring
 constexpr uint32_t kTmemCols = kAccStages * kTN;  // 256
 
+constexpr int kHeadsLd = 160;    // >= max CTAs per query tile (148), multiple of 4
+
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
@@ -67,6 +69,7 @@ struct KArgs {
     int smem_lists;   // k > 32: 1 = the per-query lists live in shared memory during the scan
     uint64_t* lists;  // [P][Bpad][k]
     uint32_t* gthr;   // [Bpad] shared per-query lower bounds on the k-th best score (ordered-float encoding)
+    uint32_t* heads;  // [Bpad][kHeadsLd] best score each CTA (slot p) has seen for the query, ordered floats, 0 = none
     float* dump;      // debug: [Bpad][dump_ld] scores, or nullptr
     int64_t dump_ld;
     uint64_t corpus_hint;
@@ -234,8 +237,66 @@ __device__ __forceinline__ uint32_t ord_of(float f) {
 __device__ __forceinline__ float ord_to_float(uint32_t o) {
     return __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o);
 }
-// lower bound published by other CTAs -> strict threshold: s > result  <=>  s >= published score
-__device__ __forceinline__ float shared_threshold(uint32_t g) { return g <= 1u ? -INFINITY : ord_to_float(g - 1u); }
+// lower bound published by other CTAs -> strict threshold: s > result  <=>  s >= published score.
+// (The predecessor of +0.0 in the ordered encoding is -0.0, which compares EQUAL to +0.0 as a float and
+// would wrongly reject exact-zero ties, so it is skipped.)
+__device__ __forceinline__ float shared_threshold(uint32_t g) {
+    if (g <= 1u) return -INFINITY;
+    uint32_t o = g - 1u;
+    if (o == 0x7FFFFFFFu) o = 0x7FFFFFFEu;
+    return ord_to_float(o);
+}
+
+// ---- cross-CTA "heads" bound (k <= 32) -----------------------------------------------------------------
+// Every CTA scanning rows for query q publishes the BEST score it has seen in heads[q][p] (a plain store to
+// its own slot, no atomics).  The k-th largest of those heads is a lower bound on the global k-th best score
+// (k different CTAs each hold a distinct row at least that good) and -- because the global top-k rows are
+// almost surely spread over different CTAs -- a tight one.  Each epilogue thread recomputes it for its query
+// at tiles 1, 4, 16, 64, ... of its CTA; after the first refresh a CTA only sees candidates that would
+// also beat the other CTAs' best rows, instead of converging its own lists from -inf
+// (k*ln(rows_per_cta/k) list updates per CTA and query).
+// The bound actually computed is slightly weaker but needs no arrays: the P slots are cut into k contiguous
+// groups and the bound is the SMALLEST group maximum (k distinct CTAs still each hold a row at least that
+// good).  Loads go out 8 x 16 bytes at a time.
+__device__ __forceinline__ uint32_t heads_bound(const uint32_t* row, int P, int k) {
+    if (P < k) return 0u;
+    uint32_t m = 0u, bound = 0xFFFFFFFFu;
+    int g = 0;
+    const int nv = (P + 3) / 4;
+    if (nv >= k) {  // group boundaries at 16-byte granularity
+#pragma unroll 1
+        for (int v0 = 0; v0 < nv; v0 += 8) {
+            uint4 w[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                w[u] = (v0 + u < nv) ? __ldcg(reinterpret_cast<const uint4*>(row) + v0 + u) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (v0 + u < nv) {
+                    const int gv = (v0 + u) * k / nv;
+                    if (gv != g) { bound = min(bound, m); m = 0u; g = gv; }
+                    m = max(max(m, max(w[u].x, w[u].y)), max(w[u].z, w[u].w));
+                }
+            }
+        }
+    } else {  // few CTAs per query (pair mode, large batches): one slot at a time
+#pragma unroll 1
+        for (int s0 = 0; s0 < P; s0 += 8) {
+            uint32_t w[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) w[u] = (s0 + u < P) ? __ldcg(row + s0 + u) : 0u;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (s0 + u < P) {
+                    const int gv = (s0 + u) * k / P;
+                    if (gv != g) { bound = min(bound, m); m = 0u; g = gv; }
+                    m = max(m, w[u]);
+                }
+            }
+        }
+    }
+    return min(bound, m);
+}
 
 // register-resident descending list: branch-free bubble insertion, no memory traffic
 template <int KREG>
@@ -268,11 +329,12 @@ __device__ __forceinline__ uint32_t pick32(const uint32_t (&v)[32], int j) {
 // Normalise fp32 queries exactly like the oracle (fp64 norm, fp32 divide), round to bf16, zero-pad to
 // [Bpad][Dp].  One warp per query row.
 __global__ void __launch_bounds__(128) k_prep_queries(const float* q, int B, int Bpad, int D, int Dp, int cosine,
-                                                      __nv_bfloat16* out, uint32_t* gthr) {
+                                                      __nv_bfloat16* out, uint32_t* gthr, uint32_t* heads) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (row >= Bpad) return;
     if (lane == 0) gthr[row] = 0u;
+    for (int j = lane; j < kHeadsLd; j += 32) heads[static_cast<size_t>(row) * kHeadsLd + j] = 0u;
     __nv_bfloat16* o = out + static_cast<size_t>(row) * Dp;
     if (row >= B) {
         for (int d = lane; d < Dp; d += 32) o[d] = __float2bfloat16_rn(0.0f);
@@ -446,6 +508,10 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
             }
             return sc;
         };
+        uint32_t* const head_row = a.heads + static_cast<size_t>(qglobal) * kHeadsLd;
+        float best_local = -INFINITY;  // best score this thread has inserted (its CTA's head for this query)
+        int tcount = 0, next_refresh = 1;
+        const int my_tiles = (a.n_tiles - p + a.P - 1) / a.P;  // tiles this CTA processes
         float sc_next[CG];
 #pragma unroll
         for (int h = 0; h < CG; ++h) sc_next[h] = row_scale(p, h);
@@ -453,7 +519,13 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
         for (int t = p; t < a.n_tiles; t += a.P) {
 #pragma unroll
             for (int h = 0; h < CG; ++h) sm_scale[as * TN + h * kTN + et] = sc_next[h];
-            if (share) thr = fmaxf(thr_local, shared_threshold(g_next));
+            if (share) thr = fmaxf(thr, fmaxf(thr_local, shared_threshold(g_next)));
+            if (KREG > 0 && share && tcount == next_refresh) {  // tiles 1, 4, 16, 64, ... of this CTA
+                if (tcount * 8 <= my_tiles)  // (not worth the L2 round trips when the CTA is almost done)
+                    thr = fmaxf(thr, shared_threshold(heads_bound(head_row, a.P, a.k)));
+                next_refresh *= 4;
+            }
+            ++tcount;
             // prefetch for the next tile of this CTA (in flight while this tile is processed)
 #pragma unroll
             for (int h = 0; h < CG; ++h) sc_next[h] = row_scale(t + a.P, h);
@@ -498,6 +570,10 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
                                 list_insert_regs<KR>(L, pack_key(s, row0 + c * 32 + j));
                                 if (L[KR - 1] != 0ull) thr_local = key_score(L[KR - 1]);
                                 thr = fmaxf(thr, thr_local);
+                                if (share && s > best_local) {  // publish this CTA's new head for the query
+                                    best_local = s;
+                                    __stcg(head_row + p, ord_of(s));
+                                }
                                 changed = true;
                             }
                         }
@@ -651,7 +727,7 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
         if (P < 1) P = 1;
         // scratch: [Qb bf16 Bpad x Dp][shared thresholds Bpad u32][lists P x Bpad x k u64]
         const size_t q_bytes = (static_cast<size_t>(Bpad) * m.Dp * 2 + 1023) / 1024 * 1024;
-        const size_t thr_bytes = (static_cast<size_t>(Bpad) * sizeof(uint32_t) + 1023) / 1024 * 1024;
+        const size_t thr_bytes = (static_cast<size_t>(Bpad) * sizeof(uint32_t) * (1 + kHeadsLd) + 1023) / 1024 * 1024;
         const size_t list_bytes = static_cast<size_t>(P) * Bpad * m.k * sizeof(uint64_t);
         const size_t need = q_bytes + thr_bytes + list_bytes;
         if (need > scratch.cap) {
@@ -665,11 +741,12 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
             scratch.cap = need + need / 2;
         }
         __nv_bfloat16* qb = reinterpret_cast<__nv_bfloat16*>(scratch.p);
-        uint32_t* gthr = reinterpret_cast<uint32_t*>(scratch.p + q_bytes);
+        uint32_t* heads = reinterpret_cast<uint32_t*>(scratch.p + q_bytes);   // [Bpad][kHeadsLd], 16-byte aligned rows
+        uint32_t* gthr = heads + static_cast<size_t>(Bpad) * kHeadsLd;           // [Bpad]
         uint64_t* lists = reinterpret_cast<uint64_t*>(scratch.p + q_bytes + thr_bytes);
 
         k_prep_queries<<<(Bpad + 3) / 4, 128, 0, m.stream>>>(m.q + static_cast<size_t>(done) * m.D, Bs, Bpad, m.D, m.Dp,
-                                                             m.cosine ? 1 : 0, qb, gthr);
+                                                             m.cosine ? 1 : 0, qb, gthr, heads);
         MMA_CUDA(cudaGetLastError());
 
         CUtensorMap tq, te;
@@ -697,6 +774,7 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
         a.smem_lists = smem_list_bytes ? 1 : 0;
         a.lists = lists;
         a.gthr = gthr;
+        a.heads = heads;
         a.dump = m.dump ? m.dump + static_cast<size_t>(done) * m.dump_ld : nullptr;
         a.dump_ld = m.dump_ld;
         a.corpus_hint = QT > 1 ? kEvictNormal : kEvictFirst;

@@ -123,6 +123,36 @@ def test_mma_predicates_and_row_offset(native, variant):
     idx.close()
 
 
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_mma_exact_zero_ties_across_ctas(native, variant):
+    """Scores that are exactly 0 (zero query, zero rows) tie across CTAs: the answer must still be the k
+    smallest row ids, whichever CTA publishes its threshold first (regression: the predecessor of +0.0 in
+    the ordered-float encoding is -0.0)."""
+    rng = np.random.default_rng(3)
+    n, D, k = 40000, 384, 10
+    x = rng.standard_normal((n, D)).astype(np.float32)
+    x[::3] = 0.0                                   # a third of the rows are all-zero (scale 0 -> score 0)
+    idx = native.NativeIndex(D)
+    idx.upsert(x)
+    q = rng.standard_normal((140, D)).astype(np.float32)
+    q[::2] = 0.0                                   # zero queries: every row scores exactly 0
+    for _ in range(10):
+        s, r, c = idx.query(q, k, path=variant_path(native, variant))
+        assert (r[::2] == np.arange(k)[None, :]).all() and (s[::2] == 0).all()
+    stored, scale, _, _ = idx.get_rows(np.arange(n))
+    check_topk(s, r, c, bf16_query_scores(stored, scale, q), None, k, tol=3e-6)
+    # a query orthogonal-ish to everything positive: make all non-zero rows score negative -> zeros win
+    neg = -np.abs(x[1:2])
+    xx = np.abs(x)
+    idx2 = native.NativeIndex(D)
+    idx2.upsert(xx)
+    for _ in range(5):
+        s2, r2, c2 = idx2.query(np.repeat(neg, 3, axis=0), k, path=variant_path(native, variant))
+        assert (r2 == np.arange(0, 3 * k, 3)[None, :]).all() and (s2 == 0).all()
+    idx.close()
+    idx2.close()
+
+
 def test_mma_ip_metric(native):
     idx, stored, scale, rng = build(native, 20000, 384, seed=13, metric=bf.METRIC_IP)
     q = rng.standard_normal((9, 384)).astype(np.float32)
