@@ -250,6 +250,7 @@ int plan_scan(cv_index* idx, QueryCtx* c, int qb, int k, bool pred, ScanLaunch* 
     ScanFn fn = pick_scan(nch, qb, pred);
     if (!fn) return fail(CV_ERR_UNSUPPORTED, "scan path: no kernel for dim=%d with %d queries per pass", idx->D, qb);
     size_t smem = (static_cast<size_t>(kSelCap) + static_cast<size_t>(kScanWarps) * qb * k) * sizeof(uint64_t);
+    if (scan_is_wide(nch)) smem += static_cast<size_t>(idx->Dp) * sizeof(float);  // the normalised query
     CV_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     int occ = 0;
     CV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kScanThreads, smem));
@@ -338,8 +339,6 @@ int enqueue_query(cv_index* idx, QueryCtx* c, cudaStream_t stream, const float* 
         }
         passes_bytes = n * (2ll * idx->Dp + 4) * ((B + 255) / 256);
     } else {
-        if (max_qb == 0)
-            return fail(CV_ERR_UNSUPPORTED, "scan path supports dim <= 1024 (got %d)", idx->D);
         int done = 0;
         while (done < B) {
             int qb = 1;

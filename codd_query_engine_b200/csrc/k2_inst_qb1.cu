@@ -1,4 +1,4 @@
-// K2 instantiations, 1 query per pass (row lengths up to 1024 elements).
+// K2 instantiations, 1 query per pass (register-resident query up to 1024 elements, wide kernel above).
 #define CV_K2_INSTANTIATE_QB 1
 #include "k2_scan.cuh"
 namespace cv {
@@ -12,7 +12,8 @@ ScanFn pick_scan_qb1(int nch, bool pred) {
         case 6: return scan_fn<6, 1>(pred);
         case 7: return scan_fn<7, 1>(pred);
         case 8: return scan_fn<8, 1>(pred);
-        default: return nullptr;
+        default:  // rows longer than 1024 elements: query in shared memory
+            return pred ? static_cast<ScanFn>(k_scan_topk_wide<true>) : static_cast<ScanFn>(k_scan_topk_wide<false>);
     }
 }
 }  // namespace cv

@@ -338,9 +338,146 @@ __global__ void __launch_bounds__(kScanThreads, (NCH * QB <= 6) ? 2 : 1) k_scan_
                                 a.q_base);
 }
 
+// K2 for long rows (Dp > 1024, up to CV_MAX_DIM): the query no longer fits the register file, so it
+// lives normalised in shared memory; a full warp owns kWideRows rows at a time and its lanes stride over
+// the rows' 16-byte chunks (each load instruction covers 512 contiguous bytes of one row).  One query per
+// launch.  Same per-warp lists, CTA merge and last-CTA global merge as the register-resident kernel.
+constexpr int kWideRows = 4;
+
+template <bool PRED>
+__global__ void __launch_bounds__(kScanThreads, 2) k_scan_topk_wide(ScanArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* selbuf = reinterpret_cast<uint64_t*>(smem_raw);          // kSelCap keys
+    uint64_t* lists = selbuf + kSelCap;                                // [warps][k]
+    float* sq = reinterpret_cast<float*>(lists + kScanWarps * a.k);    // [C * 8] normalised query, zero padded
+    __shared__ float s_norm;
+    __shared__ int s_cnt;
+    __shared__ uint64_t s_red[kScanWarps];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k = a.k, C = a.C;
+    for (int i = tid; i < C * 8; i += kScanThreads) sq[i] = i < a.D ? a.q[i] : 0.0f;
+    for (int i = tid; i < kScanWarps * k; i += kScanThreads) lists[i] = 0ull;
+    __syncthreads();
+    if (warp == 0) {
+        float nrm = 1.0f;
+        if (a.cosine) {
+            double ss = 0.0;
+            for (int d = lane; d < a.D; d += 32) {
+                double v = static_cast<double>(sq[d]);
+                ss += v * v;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(kFullMask, ss, o);
+            float n32 = static_cast<float>(sqrt(ss));
+            nrm = n32 > 0.0f ? n32 : 1.0f;
+        }
+        if (lane == 0) s_norm = nrm;
+    }
+    __syncthreads();
+    for (int i = tid; i < a.D; i += kScanThreads) sq[i] = __fdiv_rn(sq[i], s_norm);
+    __syncthreads();
+
+    uint64_t* my_list = lists + static_cast<size_t>(warp) * k;
+    uint64_t thr = 0ull;
+    const int64_t gw = static_cast<int64_t>(blockIdx.x) * kScanWarps + warp;
+    const int64_t nw = static_cast<int64_t>(gridDim.x) * kScanWarps;
+    const float4* sq4 = reinterpret_cast<const float4*>(sq);
+
+    auto process = [&](const int64_t (&rows)[kWideRows]) {
+        float acc[kWideRows];
+#pragma unroll
+        for (int r = 0; r < kWideRows; ++r) acc[r] = 0.0f;
+#pragma unroll 2
+        for (int c = lane; c < C; c += 32) {
+            uint4 w[kWideRows];
+#pragma unroll
+            for (int r = 0; r < kWideRows; ++r)
+                w[r] = rows[r] >= 0 ? ldg_stream(a.E + rows[r] * C + c) : make_uint4(0u, 0u, 0u, 0u);
+            const float4 q0 = sq4[2 * c], q1 = sq4[2 * c + 1];
+#pragma unroll
+            for (int r = 0; r < kWideRows; ++r) {
+                float s0 = fmaf(bf16lo_f32(w[r].x), q0.x, 0.0f), s1 = bf16hi_f32(w[r].x) * q0.y;
+                s0 = fmaf(bf16lo_f32(w[r].y), q0.z, s0);
+                s1 = fmaf(bf16hi_f32(w[r].y), q0.w, s1);
+                s0 = fmaf(bf16lo_f32(w[r].z), q1.x, s0);
+                s1 = fmaf(bf16hi_f32(w[r].z), q1.y, s1);
+                s0 = fmaf(bf16lo_f32(w[r].w), q1.z, s0);
+                s1 = fmaf(bf16hi_f32(w[r].w), q1.w, s1);
+                acc[r] += s0 + s1;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < kWideRows; ++r) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(kFullMask, acc[r], o);
+            if (rows[r] >= 0) {  // warp-uniform
+                const float score = acc[r] * __ldg(a.scale + rows[r]);
+                const uint64_t key = pack_key(score, a.row_offset + static_cast<uint32_t>(rows[r]));
+                if (key > thr) thr = warp_list_insert(my_list, k, key, lane);
+            }
+        }
+    };
+
+    if (!PRED) {
+        const int64_t groups = (a.n + kWideRows - 1) / kWideRows;
+        for (int64_t g = gw; g < groups; g += nw) {
+            int64_t rows[kWideRows];
+#pragma unroll
+            for (int r = 0; r < kWideRows; ++r) {
+                const int64_t row = g * kWideRows + r;
+                rows[r] = row < a.n ? row : -1;
+            }
+            process(rows);
+        }
+    } else {
+        const int64_t blocks = (a.n + 127) / 128;
+        const int64_t nwords = (a.n + 31) / 32;
+        for (int64_t blk = gw; blk < blocks; blk += nw) {
+            const int64_t base = blk * 128;
+            uint32_t words[4];
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const int64_t r = base + 32 * w + lane;
+                bool ok = r < a.n;
+                if (ok && a.ns_code != kAny) ok = __ldg(a.ns + r) == a.ns_code;
+                if (ok && a.label_code != kAny) ok = __ldg(a.label + r) == a.label_code;
+                uint32_t word = __ballot_sync(kFullMask, ok);
+                if (a.mask) {
+                    const int64_t wi = (base >> 5) + w;
+                    word &= (wi < nwords) ? __ldg(a.mask + wi) : 0u;
+                }
+                words[w] = word;
+            }
+            int remaining = __popc(words[0]) + __popc(words[1]) + __popc(words[2]) + __popc(words[3]);
+            while (remaining > 0) {
+                int64_t rows[kWideRows];
+#pragma unroll
+                for (int r = 0; r < kWideRows; ++r) {
+                    int64_t row = -1;
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        if (row < 0 && words[w]) {
+                            const int bit = __ffs(words[w]) - 1;
+                            words[w] &= words[w] - 1;
+                            row = base + 32 * w + bit;
+                        }
+                    }
+                    rows[r] = row;
+                }
+                remaining -= kWideRows;
+                process(rows);
+            }
+        }
+    }
+    publish_and_final_merge<1>(lists, kScanWarps, k, a.partial, a.counter, a.out, selbuf, &s_cnt, s_red, a.px, a.seq,
+                               a.q_base);
+}
+
 using ScanFn = void (*)(ScanArgs);
 // largest query-block size the register-resident K2 supports for a row of nch*16 16-byte chunks
-inline int scan_max_qb(int nch) { return nch <= 3 ? 4 : nch <= 6 ? 2 : nch <= 8 ? 1 : 0; }
+inline int scan_max_qb(int nch) { return nch <= 3 ? 4 : nch <= 6 ? 2 : 1; }  // nch > 8: wide kernel, 1 query
+inline bool scan_is_wide(int nch) { return nch > 8; }
 ScanFn pick_scan_qb1(int nch, bool pred);
 ScanFn pick_scan_qb2(int nch, bool pred);
 ScanFn pick_scan_qb4(int nch, bool pred);

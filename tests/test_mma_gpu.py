@@ -165,7 +165,7 @@ def test_mma_unsupported_dim_is_loud_and_auto_falls_to_scan(native):
     idx, stored, scale, rng = build(native, 2000, 1024, seed=14)
     q = rng.standard_normal((8, 1024)).astype(np.float32)
     with pytest.raises(native.NativeError):
-        idx.query(q, 5, path=native.PATH_MMA)
+        idx.query(q, 5, path=native.PATH_MMA)     # no 1024-d query tile fits shared memory
     s, r, c = idx.query(q, 5)  # AUTO
     assert idx.stats().last_path == native.PATH_SCAN
     check_topk(s, r, c, oracle_full_scores(stored, scale, q), None, 5, tol=2e-6)

@@ -78,6 +78,33 @@ def test_scan_parity(native, D, B, k):
     idx.close()
 
 
+@pytest.mark.parametrize("D,B,k", [(1100, 1, 10), (1536, 2, 10), (2048, 1, 50), (3072, 3, 5), (4096, 1, 128)])
+def test_scan_wide_rows_parity(native, D, B, k):
+    """Rows longer than 1024 elements take the wide kernel (query in shared memory)."""
+    rng = np.random.default_rng(D + B + k)
+    n = 20011
+    x = rng.standard_normal((n, D)).astype(np.float32)
+    x[100] = x[7]
+    ns = rng.integers(1, 5, n).astype(np.uint32)
+    q = rng.standard_normal((B, D)).astype(np.float32)
+    idx = native.NativeIndex(D)
+    idx.upsert(x, ns_codes=ns)
+    stored, scale, _, _ = stored_of(idx)
+    est, esc = bf.normalise_store(x)
+    assert np.array_equal(stored, est) and np.array_equal(scale, esc)
+    full = oracle_full_scores(stored, scale, q)
+    s, r, c = idx.query(q, k)  # AUTO: no tensor path above 768 -> wide scan
+    assert idx.stats().last_path == native.PATH_SCAN
+    check_topk(s, r, c, full, None, k, tol=4e-6)
+    s, r, c = idx.query(q, k, ns_code=2)
+    check_topk(s, r, c, full, ns == 2, k, tol=4e-6)
+    bits = rng.random(n) < 0.02
+    words = np.packbits(np.concatenate([bits, np.zeros((-n) % 32, bool)]), bitorder="little").view(np.uint32)
+    s, r, c = idx.query(q, k, mask=words)
+    check_topk(s, r, c, full, bits, k, tol=4e-6)
+    idx.close()
+
+
 @pytest.mark.parametrize("n", [0, 1, 2, 5, 9, 33, 127, 128, 129, 1000])
 def test_scan_small_and_ragged(native, n):
     rng = np.random.default_rng(n)

@@ -23,7 +23,7 @@ def native(native_lib):
 @settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
 @given(data=st.data())
 def test_random_shapes_match_oracle(native, data):
-    D = data.draw(st.sampled_from([8, 24, 64, 100, 128, 384, 520, 768]))
+    D = data.draw(st.sampled_from([8, 24, 64, 100, 128, 384, 520, 768, 1500]))
     n = data.draw(st.integers(1, 3000))
     B = data.draw(st.integers(1, 9))
     k = data.draw(st.sampled_from([1, 2, 5, 10, 33, 100, 128]))
