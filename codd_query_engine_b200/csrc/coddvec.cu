@@ -205,7 +205,9 @@ int acquire_ctx(cv_index* idx, QueryCtx** out) {
     CV_CUDA(cudaEventCreate(&c->t0));
     CV_CUDA(cudaEventCreate(&c->t1));
     CV_CUDA(cudaMalloc(&c->d_counter, 64 * sizeof(unsigned int)));
-    CV_CUDA(cudaMemset(c->d_counter, 0, 64 * sizeof(unsigned int)));
+    // stream-ordered: the context's streams are non-blocking, so a NULL-stream cudaMemset would not be
+    // ordered before the first kernel that uses the counter; `busy` carries the dependency to any stream
+    CV_CUDA(cudaMemsetAsync(c->d_counter, 0, 64 * sizeof(unsigned int), c->stream));
     CV_CUDA(cudaEventRecord(c->busy, c->stream));
     {
         std::lock_guard<std::mutex> g(idx->ctx_mu);

@@ -41,7 +41,7 @@ constexpr int kBlockBytes = kTN * kKB * 2;  // 16 KiB: one [128 rows][64] bf16 b
 constexpr int kMaxStages = 8;    // corpus ring depth: as many 16 KiB stages as fit next to the query tile (<= 8)
 constexpr int kAccStages = 2;
 constexpr int kThreads = 192;
-constexpr int kMaxKBlocks = 12;  // Dp <= 768: the query tile (<= 192 KiB) stays resident next to a >= 2-stage ring
+constexpr int kMaxKBlocks = 64;  // Dp <= 4096 (CV_MAX_DIM)
 constexpr uint32_t kTmemCols = kAccStages * kTN;  // 256
 
 constexpr int kHeadsLd = 160;    // >= max CTAs per query tile (148), multiple of 4
@@ -59,6 +59,8 @@ struct KArgs {
     int64_t n;
     int kblocks;
     int stages;     // ring depth actually used (<= kMaxStages)
+    int q_resident; // 1: the query tile stays in shared memory for the whole kernel (short rows);
+                    // 0: its K blocks are streamed through the ring next to the corpus blocks (long rows)
     int k;
     uint32_t row_offset;
     int n_tiles;
@@ -372,10 +374,14 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
     constexpr uint32_t kCols = kAccStages * TN;        // TMEM columns: 256 (CG=1) / 512 (CG=2)
     extern __shared__ __align__(1024) unsigned char smem[];
     // carve-up (all block bases 1024-byte aligned, as SWIZZLE_128B requires)
-    unsigned char* sm_q = smem;                                           // kblocks x 16 KiB (own 128 queries)
-    unsigned char* sm_ring = smem + static_cast<size_t>(a.kblocks) * kBlockBytes;  // kStages x 16 KiB (own 128 rows)
+    // q_resident: [query tile: kblocks x 16 KiB][ring: stages x 16 KiB corpus blocks]
+    // streamed:   [ring: stages x (16 KiB query block + 16 KiB corpus block)]
+    const bool qres = a.q_resident != 0;
     const int kStages = a.stages;
-    float* sm_scale = reinterpret_cast<float*>(sm_ring + static_cast<size_t>(kStages) * kBlockBytes);  // [2][TN]
+    const uint32_t stage_bytes = qres ? kBlockBytes : 2 * kBlockBytes;
+    unsigned char* sm_q = smem;
+    unsigned char* sm_ring = smem + (qres ? static_cast<size_t>(a.kblocks) * kBlockBytes : 0);
+    float* sm_scale = reinterpret_cast<float*>(sm_ring + static_cast<size_t>(kStages) * stage_bytes);  // [2][TN]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm_scale + kAccStages * TN);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1 + 2 * kAccStages);
     uint64_t* sm_lists = reinterpret_cast<uint64_t*>(tmem_slot + 4);  // [128][k] when a.smem_lists
@@ -417,21 +423,29 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
         if (lane == 0) {
             tma_prefetch_desc(&tmap_q);
             tma_prefetch_desc(&tmap_e);
-            const uint32_t q_bytes = static_cast<uint32_t>(a.kblocks) * kBlockBytes;
-            if (rank == 0) mbar_arrive_expect_tx(bar_q, q_bytes * CG);
-            else mbar_arrive_cluster(bar_q, 0);
-            for (int kb = 0; kb < a.kblocks; ++kb)
-                tma_load_2d<CG>(smem_u32(sm_q + static_cast<size_t>(kb) * kBlockBytes), &tmap_q, bar_q, kb * kKB,
-                                (qt * CG + static_cast<int>(rank)) * kQ, kEvictLast);
+            const int q_row = (qt * CG + static_cast<int>(rank)) * kQ;
+            if (qres) {
+                const uint32_t q_bytes = static_cast<uint32_t>(a.kblocks) * kBlockBytes;
+                if (rank == 0) mbar_arrive_expect_tx(bar_q, q_bytes * CG);
+                else mbar_arrive_cluster(bar_q, 0);
+                for (int kb = 0; kb < a.kblocks; ++kb)
+                    tma_load_2d<CG>(smem_u32(sm_q + static_cast<size_t>(kb) * kBlockBytes), &tmap_q, bar_q, kb * kKB, q_row,
+                                    kEvictLast);
+            }
             int stage = 0;
             uint32_t phase = 0;
             for (int t = p; t < a.n_tiles; t += a.P) {
                 for (int kb = 0; kb < a.kblocks; ++kb) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                    if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, kBlockBytes * CG);
+                    if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, stage_bytes * CG);
                     else mbar_arrive_cluster(bar_full + 8 * stage, 0);
-                    tma_load_2d<CG>(smem_u32(sm_ring + static_cast<size_t>(stage) * kBlockBytes), &tmap_e,
-                                    bar_full + 8 * stage, kb * kKB, t * TN + static_cast<int>(rank) * kTN, a.corpus_hint);
+                    unsigned char* slot = sm_ring + static_cast<size_t>(stage) * stage_bytes;
+                    if (!qres) {  // this K block of the query tile rides along (L2 resident, evict-last)
+                        tma_load_2d<CG>(smem_u32(slot), &tmap_q, bar_full + 8 * stage, kb * kKB, q_row, kEvictLast);
+                        slot += kBlockBytes;
+                    }
+                    tma_load_2d<CG>(smem_u32(slot), &tmap_e, bar_full + 8 * stage, kb * kKB,
+                                    t * TN + static_cast<int>(rank) * kTN, a.corpus_hint);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -440,8 +454,10 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
         // ===================================================================== MMA issuer (leader CTA only)
         if (lane == 0 && rank == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(kQ * CG, TN);
-            mbar_wait(bar_q, 0);
-            tc_fence_after();
+            if (qres) {
+                mbar_wait(bar_q, 0);
+                tc_fence_after();
+            }
             int stage = 0, as = 0;
             uint32_t phase = 0, aphase = 0;
             for (int t = p; t < a.n_tiles; t += a.P) {
@@ -451,8 +467,9 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
                 for (int kb = 0; kb < a.kblocks; ++kb) {
                     mbar_wait(bar_full + 8 * stage, phase);  // TMA bytes of every CTA in the group have landed
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(sm_q + static_cast<size_t>(kb) * kBlockBytes);
-                    const uint32_t b_addr = smem_u32(sm_ring + static_cast<size_t>(stage) * kBlockBytes);
+                    const uint32_t slot = smem_u32(sm_ring + static_cast<size_t>(stage) * stage_bytes);
+                    const uint32_t a_addr = qres ? smem_u32(sm_q + static_cast<size_t>(kb) * kBlockBytes) : slot;
+                    const uint32_t b_addr = qres ? slot : slot + kBlockBytes;
 #pragma unroll
                     for (int ks = 0; ks < kKB / 16; ++ks)  // UMMA_K = 16 bf16 = 32 bytes inside the swizzle row
                         umma_bf16<CG>(tmem_d, umma_desc_sw128(a_addr + ks * 32), umma_desc_sw128(b_addr + ks * 32), idesc,
@@ -640,14 +657,15 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
 
 constexpr size_t kSmemLimit = 232448;  // 227 KiB: the per-CTA maximum on sm_100
 
-size_t mma_smem_bytes(int kblocks, int stages, int cg, size_t list_bytes) {
-    return static_cast<size_t>(kblocks + stages) * kBlockBytes + kAccStages * kTN * cg * sizeof(float) +
+size_t mma_smem_bytes(int kblocks, int stages, int cg, size_t list_bytes, bool q_resident) {
+    const size_t blocks = q_resident ? static_cast<size_t>(kblocks + stages) : 2 * static_cast<size_t>(stages);
+    return blocks * kBlockBytes + kAccStages * kTN * cg * sizeof(float) +
            (2 * kMaxStages + 1 + 2 * kAccStages) * sizeof(uint64_t) + 16 + list_bytes;
 }
 
-int mma_stages(int kblocks, int cg, size_t list_bytes) {
+int mma_stages(int kblocks, int cg, size_t list_bytes, bool q_resident) {
     int s = kMaxStages;
-    while (s > 2 && mma_smem_bytes(kblocks, s, cg, list_bytes) > kSmemLimit) --s;
+    while (s > 1 && mma_smem_bytes(kblocks, s, cg, list_bytes, q_resident) > kSmemLimit) --s;
     return s;
 }
 
@@ -699,7 +717,7 @@ std::string& mma_error() { return g_mma_err; }
 
 int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* launches) {
     if (!mma_supported(m.Dp))
-        return mma_fail(CV_ERR_UNSUPPORTED, "tensor-core path supports padded dim <= 768 (got " + std::to_string(m.Dp) + ")");
+        return mma_fail(CV_ERR_UNSUPPORTED, "tensor-core path supports padded dim <= 4096 (got " + std::to_string(m.Dp) + ")");
     const int kblocks = m.Dp / kKB;
     // CTA pairs (cta_group::2, 256 queries x 256 rows per tile) once a batch fills more than one
     // 128-query tile; single CTAs below that (the scan is HBM-bound there and pairs would idle lanes).
@@ -709,9 +727,12 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
     const int units = m.sm_count / cg;  // CTAs or CTA pairs that fit the chip
     // k > 32: per-query lists go to shared memory if a >= 3-stage ring still fits beside them
     size_t smem_list_bytes = m.k > 32 && !m.dump ? static_cast<size_t>(kQ) * m.k * sizeof(uint64_t) : 0;
-    if (smem_list_bytes && mma_smem_bytes(kblocks, 3, cg, smem_list_bytes) > kSmemLimit) smem_list_bytes = 0;
-    const int stages = mma_stages(kblocks, cg, smem_list_bytes);
-    const size_t smem = mma_smem_bytes(kblocks, stages, cg, smem_list_bytes);
+    // Short rows keep the query tile resident (a deep corpus-only ring); long rows stream the query's K
+    // blocks through the ring with the corpus blocks (7 x 32 KiB stages) -- the tile would crowd the ring out.
+    bool q_resident = mma_smem_bytes(kblocks, 6, cg, 0, true) <= kSmemLimit;
+    if (smem_list_bytes && mma_smem_bytes(kblocks, 3, cg, smem_list_bytes, q_resident) > kSmemLimit) smem_list_bytes = 0;
+    const int stages = mma_stages(kblocks, cg, smem_list_bytes, q_resident);
+    const size_t smem = mma_smem_bytes(kblocks, stages, cg, smem_list_bytes, q_resident);
     if (smem > kSmemLimit)
         return mma_fail(CV_ERR_UNSUPPORTED, "tensor-core path: query tile does not fit shared memory at dim " + std::to_string(m.Dp));
     MmaKernel kernel = cg == 2 ? pick_mma_kernel<2>(m.dump != nullptr, m.k) : pick_mma_kernel<1>(m.dump != nullptr, m.k);
@@ -764,6 +785,7 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
         a.n = m.n;
         a.kblocks = kblocks;
         a.stages = stages;
+        a.q_resident = q_resident ? 1 : 0;
         a.k = m.k;
         a.row_offset = m.row_offset;
         a.n_tiles = n_tiles;

@@ -161,14 +161,19 @@ def test_mma_ip_metric(native):
     idx.close()
 
 
-def test_mma_unsupported_dim_is_loud_and_auto_falls_to_scan(native):
-    idx, stored, scale, rng = build(native, 2000, 1024, seed=14)
-    q = rng.standard_normal((8, 1024)).astype(np.float32)
-    with pytest.raises(native.NativeError):
-        idx.query(q, 5, path=native.PATH_MMA)     # no 1024-d query tile fits shared memory
-    s, r, c = idx.query(q, 5)  # AUTO
-    assert idx.stats().last_path == native.PATH_SCAN
-    check_topk(s, r, c, oracle_full_scores(stored, scale, q), None, 5, tol=2e-6)
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("D,B,k", [(768, 40, 10), (1024, 8, 10), (1536, 150, 10), (2048, 17, 20), (4096, 5, 10)])
+def test_mma_long_rows_stream_the_query_tile(native, D, B, k, variant):
+    """Above 512-d the query tile no longer stays resident: its K blocks ride through the TMA ring."""
+    idx, stored, scale, rng = build(native, 9000, D, seed=D + B)
+    q = rng.standard_normal((B, D)).astype(np.float32)
+    got = idx.debug_mma_scores(q, path=variant_path(native, variant))
+    assert np.abs(got - bf16_query_scores(stored, scale, q)).max() <= 5e-6
+    s, r, c = idx.query(q, k, path=variant_path(native, variant))
+    check_topk(s, r, c, bf16_query_scores(stored, scale, q), None, k, tol=5e-6)
+    check_topk(s, r, c, oracle_full_scores(stored, scale, q), None, k, tol=TOL)
+    s2, r2, c2 = idx.query(q, k)  # AUTO takes the tensor path for batches at every dimension
+    assert idx.stats().last_path == native.PATH_MMA
     idx.close()
 
 

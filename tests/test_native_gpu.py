@@ -93,14 +93,14 @@ def test_scan_wide_rows_parity(native, D, B, k):
     est, esc = bf.normalise_store(x)
     assert np.array_equal(stored, est) and np.array_equal(scale, esc)
     full = oracle_full_scores(stored, scale, q)
-    s, r, c = idx.query(q, k)  # AUTO: no tensor path above 768 -> wide scan
+    s, r, c = idx.query(q, k, path=native.PATH_SCAN)
     assert idx.stats().last_path == native.PATH_SCAN
     check_topk(s, r, c, full, None, k, tol=4e-6)
-    s, r, c = idx.query(q, k, ns_code=2)
+    s, r, c = idx.query(q, k, ns_code=2, path=native.PATH_SCAN)
     check_topk(s, r, c, full, ns == 2, k, tol=4e-6)
     bits = rng.random(n) < 0.02
     words = np.packbits(np.concatenate([bits, np.zeros((-n) % 32, bool)]), bitorder="little").view(np.uint32)
-    s, r, c = idx.query(q, k, mask=words)
+    s, r, c = idx.query(q, k, mask=words, path=native.PATH_SCAN)
     check_topk(s, r, c, full, bits, k, tol=4e-6)
     idx.close()
 
