@@ -292,9 +292,9 @@ int enqueue_query(cv_index* idx, QueryCtx* c, cudaStream_t stream, const float* 
     const int max_qb = scan_max_qb(nch);
     if (path == CV_PATH_AUTO) {
         // B = 1: fp32-exact K2 scan.  Batches: K3 on the tensor cores, except where K3 has no fast top-k
-        // (k > 32 keeps lists in global memory) and the batch is small enough for a few K2 passes.
+        // (k > 64 keeps lists in shared / global memory) and the batch is small enough for a few K2 passes.
         const bool scan = B <= std::min(max_qb, kAutoScanMaxBatch) || !mma_supported(idx->Dp) ||
-                          (k > 32 && max_qb > 0 && B <= 4 * max_qb);
+                          (k > 64 && max_qb > 0 && B <= 4 * max_qb);
         path = scan ? CV_PATH_SCAN : CV_PATH_MMA;
     }
     const bool timed = idx->profiling.load() != 0;

@@ -676,6 +676,7 @@ MmaKernel pick_mma_kernel(bool dump, int k) {
     if (dump) return k_mma_topk<true, 0, CG>;
     if (k <= 16) return k_mma_topk<false, 16, CG>;
     if (k <= 32) return k_mma_topk<false, 32, CG>;
+    if (k <= 64) return k_mma_topk<false, 64, CG>;
     return k_mma_topk<false, 0, CG>;
 }
 
@@ -726,7 +727,7 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
     const int n_tiles = static_cast<int>((m.n + tile_rows - 1) / tile_rows);
     const int units = m.sm_count / cg;  // CTAs or CTA pairs that fit the chip
     // k > 32: per-query lists go to shared memory if a >= 3-stage ring still fits beside them
-    size_t smem_list_bytes = m.k > 32 && !m.dump ? static_cast<size_t>(kQ) * m.k * sizeof(uint64_t) : 0;
+    size_t smem_list_bytes = m.k > 64 && !m.dump ? static_cast<size_t>(kQ) * m.k * sizeof(uint64_t) : 0;
     // Short rows keep the query tile resident (a deep corpus-only ring); long rows stream the query's K
     // blocks through the ring with the corpus blocks (7 x 32 KiB stages) -- the tile would crowd the ring out.
     bool q_resident = mma_smem_bytes(kblocks, 6, cg, 0, true) <= kSmemLimit;
