@@ -18,7 +18,7 @@ from __future__ import annotations
 import json
 import threading
 from concurrent.futures import Future
-from typing import Any, Optional
+from typing import Any
 
 import numpy as np
 

@@ -36,7 +36,7 @@ import numpy as np
 from . import native
 from .embedding import default_embedding_function
 from .native import NativeIndex
-from .where import ANY, compile_where, evaluate, validate_where
+from .where import compile_where, evaluate, validate_where
 
 DEFAULT_LABEL_FIELD = "category"
 _QUERY_INCLUDE = ("metadatas", "documents", "distances")
