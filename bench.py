@@ -198,8 +198,8 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": per_step_full * 1e3, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "bf16 rows x fp32 query, fp32 accumulate", "data": "synthetic",
-        "config": workload_config(args),
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": dict(workload_config(args), arithmetic="bf16 rows x fp32 query, fp32 accumulate (CPU oracle port)"),
         "cpu_baseline": {"value": qps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample_txt},
         "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -349,8 +349,10 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "bf16 rows x fp32 query, fp32 accumulate" if used_path != native.PATH_MMA else "bf16 x bf16, fp32 accumulate",
-        "data": "synthetic", "config": workload_config(args),
+        "dtype": "bf16",
+        "data": "synthetic",
+        "config": dict(workload_config(args), arithmetic="bf16 rows x fp32 query, fp32 accumulate (K2 scan)"
+                       if used_path != native.PATH_MMA else "bf16 rows x bf16 queries on tcgen05, fp32 accumulate in TMEM (K3)"),
         "roofline": roof,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": B * k * 8,
                 "api": "ShardedIndex.query -> cv_query_device (C-ABI) with pinned host buffers"},
