@@ -40,7 +40,8 @@ class _StubFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
 
 
 def main():
-    sys.path[:0] = [os.path.join(ROOT, "shim"), ROOT, REF]
+    # (codd_lib is a nested project: REF/codd_lib/codd_lib is the importable package)
+    sys.path[:0] = [os.path.join(ROOT, "shim"), ROOT, os.path.join(REF, "codd_lib"), REF]
     sys.meta_path.append(_StubFinder())
     if "--native" not in sys.argv:
         from codd_query_engine_b200 import client as client_mod
@@ -73,6 +74,32 @@ def main():
             print("PASS", rel.split("/")[-1], name)
     print(f"reference tests passed against the drop-in: {ran}")
     assert ran == 9, ran
+    check_client_projection(chromadb)
+
+
+def check_client_projection(chromadb):
+    """codd_lib's MetricsPromQLClient.search_relevant_metrics (the dict ->
+    SearchResult projection the service and CLI call) on top of the reference store on top of the drop-in."""
+    try:
+        from codd_lib.client.metrics_promql_client import MetricsPromQLClient
+    except Exception as exc:  # codd_lib pulls in the LLM stack; skip if the stubs are not enough
+        print("SKIP codd_lib projection:", type(exc).__name__, exc)
+        return
+    from codd_dal.metrics.metrics_semantic_metadata_store import MetricsSemanticMetadataStore
+
+    store = MetricsSemanticMetadataStore(chromadb.HttpClient(host="localhost", port=8000), collection_name="a7")
+    store.index_metadata("prod", {"metric_name": "http.latency", "type": "histogram",
+                                  "description": "HTTP request latency in milliseconds", "unit": "ms",
+                                  "golden_signal_type": "latency"})
+    store.index_metadata("prod", {"metric_name": "db.connections", "description": "Active database connections"})
+    fake_self = types.SimpleNamespace(semantic_metadata_store=store)
+    hits = MetricsPromQLClient.search_relevant_metrics(fake_self, "request latency", limit=2)
+    assert [h["metric_name"] for h in hits] == ["http.latency", "db.connections"]
+    assert set(hits[0]) == {"metric_name", "similarity_score", "description", "unit", "category", "subcategory",
+                            "category_description", "golden_signal_type", "golden_signal_description", "meter_type",
+                            "meter_type_description"}
+    assert hits[0]["unit"] == "ms" and 0 <= hits[0]["similarity_score"] <= 1
+    print("PASS codd_lib MetricsPromQLClient.search_relevant_metrics over the drop-in")
 
 
 if __name__ == "__main__":
