@@ -75,6 +75,40 @@ def main():
     print(f"reference tests passed against the drop-in: {ran}")
     assert ran == 9, ran
     check_client_projection(chromadb)
+    check_indexer_job(chromadb)
+
+
+def check_indexer_job(chromadb):
+    """the indexer job's per-metric loop (`_process_batch`: metric_exists ->
+    enrich -> index_metadata, codd_jobs/metrics_semantic_indexer_job.py:359-461) over the drop-in, with the
+    LLM enrichment agent replaced by a canned one (the LLM is out of scope, the store calls are not)."""
+    try:
+        from codd_jobs.metrics_semantic_indexer_job import IndexingStats, MetricsSemanticIndexerJob
+    except Exception as exc:
+        print("SKIP indexer job:", type(exc).__name__, exc)
+        return
+    from codd_dal.metrics.metrics_semantic_metadata_store import MetricsSemanticMetadataStore
+
+    class CannedAgent:
+        def enrich_metric_to_dict(self, metric_name, metric_type, description=None):
+            return {"metric_name": metric_name, "type": metric_type, "description": description or metric_name,
+                    "category": "application", "golden_signal_type": "latency" if "latency" in metric_name else "traffic",
+                    "meter_type": metric_type}
+
+    job = object.__new__(MetricsSemanticIndexerJob)
+    job.semantic_store = MetricsSemanticMetadataStore(chromadb.HttpClient(host="localhost", port=8001))
+    job.enrichment_agent = CannedAgent()
+    job.stats = IndexingStats()
+    batch = [{"metric": "http_request_latency_seconds", "type": "histogram", "help": "HTTP request latency"},
+             {"metric": "http_requests_total", "type": "counter", "help": "Total HTTP requests"},
+             {"metric": "bad metric name", "type": "gauge", "help": "rejected by the store's validation"}]
+    job._process_batch("prod", batch, 1, 1, skip_if_present=True)
+    assert (job.stats.indexed_metrics, job.stats.failed_metrics, job.stats.skipped_metrics) == (2, 1, 0), job.stats
+    job._process_batch("prod", batch[:2], 1, 1, skip_if_present=True)   # second run: already present
+    assert job.stats.skipped_metrics == 2 and job.stats.indexed_metrics == 2
+    hits = job.semantic_store.search_metadata("request latency", n_results=2)
+    assert hits[0]["metric_name"] == "http_request_latency_seconds" and hits[0]["namespace"] == "prod"
+    print("PASS codd_jobs MetricsSemanticIndexerJob._process_batch over the drop-in")
 
 
 def check_client_projection(chromadb):

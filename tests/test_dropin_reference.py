@@ -25,3 +25,4 @@ def test_reference_store_and_its_tests_run_on_the_dropin():
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "reference tests passed against the drop-in: 9" in out.stdout
     assert "PASS codd_lib MetricsPromQLClient.search_relevant_metrics" in out.stdout
+    assert "PASS codd_jobs MetricsSemanticIndexerJob._process_batch" in out.stdout
