@@ -365,6 +365,7 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_extras:
         line["cpu_baseline"] = cpu_baseline(args, index, q_host)
         line["configs"] = sweep_small_configs(torch, native, D, k, pk)
+        line["reference_case"] = reference_case(torch, native, D, k)
     if rank == 0:
         print(json.dumps(line))
     index.close()
@@ -429,6 +430,53 @@ def sweep_small_configs(torch, native, D, k, pk):
     except Exception as exc:
         out.append({"error": str(exc)})
     return out
+
+
+def reference_case(torch, native, D, k, rows=10_000, nq=200):
+    """BASELINE.json configs[0], the reference's own CPU-runnable case: 10k metric embeddings, one query
+    at a time, top-10.  Timed: this package (host buffers in and out through the C-ABI), the exact CPU
+    oracle, and the HNSW restatement with the reference's parameters (oracle/hnsw.c, one thread, one query
+    per call as store.py:314-316 issues them).  Reported separately, as the north-star asks: recall@k of
+    the approximate graph answer and of this package's answer against the exact brute force."""
+    try:
+        from oracle import brute_force as bf  # checker / baseline only
+        from oracle import hnsw
+
+        rng = np.random.default_rng(0)
+        x = rng.standard_normal((rows, D), dtype=np.float32)
+        qs = rng.standard_normal((nq, D), dtype=np.float32)
+        idx = native.NativeIndex(D, capacity_rows=rows, max_rows=rows)
+        idx.upsert(x)
+        for i in range(20):
+            idx.query(qs[i:i + 1], k)
+        t0 = time.perf_counter()
+        ours = [idx.query(qs[i:i + 1], k)[1][0] for i in range(nq)]
+        t_ours = (time.perf_counter() - t0) / nq
+        stored, scale, _, _ = idx.get_rows(np.arange(rows))
+        idx.close()
+        lib = load_c_oracle()
+        cpu_time_queries(lib, stored, scale, qs[:1], k, 5)
+        t_bf, threads, _ = cpu_time_queries(lib, stored, scale, qs[:1], k, 200)
+        _, exact = bf.unpack_keys(cpu_time_queries(lib, stored, scale, qs, k, 1)[2])
+        t0 = time.perf_counter()
+        graph = hnsw.HnswIndex(D, rows)
+        graph.add(x)
+        t_graph = time.perf_counter() - t0
+        graph.search(qs[:20], k)
+        t0 = time.perf_counter()
+        approx = np.concatenate([graph.search(qs[i:i + 1], k, threads=1)[0] for i in range(nq)])
+        t_hnsw = (time.perf_counter() - t0) / nq
+        graph.close()
+        return {"workload": f"{rows} x {D} metric embeddings, 1 query per call, top-{k} (BASELINE.json configs[0]); "
+                            f"iid Gaussian rows (the graph walk's worst case)",
+                "ours_e2e_ms_per_query": t_ours * 1e3, "ours_e2e_qps": 1 / t_ours,
+                "cpu_exact_oracle_ms_per_query": float(np.median(t_bf)) * 1e3, "cpu_exact_oracle_threads": threads,
+                "cpu_hnsw_port_ms_per_query": t_hnsw * 1e3, "cpu_hnsw_port_qps": 1 / t_hnsw, "cpu_hnsw_port_threads": 1,
+                "cpu_hnsw_port_build_s": t_graph, "hnsw_params": "cosine, M=16, ef_construction=200, ef_search=100",
+                "recall_at_k_hnsw_vs_exact": hnsw.recall_at_k(approx, exact),
+                "recall_at_k_ours_vs_exact": hnsw.recall_at_k(np.array(ours), exact), "recall_queries": nq}
+    except Exception as exc:  # reported, never required
+        return {"error": str(exc)}
 
 
 def main():

@@ -2,6 +2,8 @@
 """Parity-checked measurement of the secondary BASELINE.json configs on one B200 (lives under tests/ because
 it uses the oracle as its checker) (bench.py covers configs[1] and the 100M corpus):
 
+  cfg1  the reference's CPU-runnable case: 10k x 384 in the semantic store, 1 query, top-10 -- end to end through
+        Collection.query / search_metadata, beside the exact CPU oracle and the HNSW restatement (timing + recall@k)
   cfg3  10M x 768 bf16, fused namespace predicate at 10 % selectivity, top-50, batch 1 (K2 PRED)
   cfg5  bulk upsert of 1M x 384 fp32 host embeddings in chunks of 1000 (MAX_BULK_OPERATIONS,
         codd_dal/metrics/metrics_semantic_metadata_store.py:23) interleaved with live top-10 queries
@@ -186,6 +188,43 @@ def cfg1(rows=10_000):
     os_, or_ = bf.unpack_keys(okeys)
     parity = [f"ns#metric.{r}" for r in or_[0]] == res["ids"][0] and bool(np.allclose(1 - os_[0], res["distances"][0], atol=2e-6))
     shape_ok = len(hits) == k and all("similarity_score" in h and h["namespace"] == "ns" for h in hits)
+    # The reference's own index type on the same vectors: HNSW (cosine, M=16, ef 200/100 -- store.py:63-68),
+    # restated in oracle/hnsw.c.  Reported: its single-thread query time (one query per call, as the reference
+    # issues them) and recall@k of its answer / of this package's answer against the exact brute force.
+    from oracle import hnsw  # checker / baseline only
+    nq = 200
+    qs = rng.standard_normal((nq, D), dtype=np.float32)
+    t0 = time.perf_counter()
+    graph = hnsw.HnswIndex(D, rows)
+    graph.add(x)
+    t_graph = time.perf_counter() - t0
+    graph.search(qs[:20], k)
+    t0 = time.perf_counter()
+    h_ids, _ = graph.search(qs, k, threads=1)
+    t_hnsw = (time.perf_counter() - t0) / nq
+    ex_keys = bench.cpu_time_queries(lib, stored, scale, qs, k, 1)[2]
+    _, ex_rows = bf.unpack_keys(ex_keys)
+    ours = coll.query(query_embeddings=qs, n_results=k, include=[])
+    our_rows = np.array([[int(i.rsplit(".", 1)[1]) for i in row] for row in ours["ids"]])
+    recall_hnsw = hnsw.recall_at_k(h_ids, ex_rows)
+    recall_ours = hnsw.recall_at_k(our_rows, ex_rows)
+    graph.close()
+    # clustered variant (256 Gaussian centroids, sigma 0.3 -- SURVEY.md section 8d): embeddings with structure, where
+    # the graph walk does well; iid Gaussian rows above are its worst case
+    cent = rng.standard_normal((256, D), dtype=np.float32)
+    xc = cent[rng.integers(0, 256, rows)] + 0.3 * rng.standard_normal((rows, D), dtype=np.float32)
+    qc = cent[rng.integers(0, 256, nq)] + 0.3 * rng.standard_normal((nq, D), dtype=np.float32)
+    graph = hnsw.HnswIndex(D, rows)
+    graph.add(xc)
+    hc_ids, _ = graph.search(qc, k, threads=1)
+    graph.close()
+    cst, csc = bf.normalise_store(xc)
+    _, exc_rows = bf.unpack_keys(bench.cpu_time_queries(lib, cst, csc, qc, k, 1)[2])
+    cl = client.get_or_create_collection("cfg1_clustered")
+    cl.upsert(ids=[f"c.{i}" for i in range(rows)], embeddings=xc)
+    oc = cl.query(query_embeddings=qc, n_results=k, include=[])
+    oc_rows = np.array([[int(i.rsplit(".", 1)[1]) for i in row] for row in oc["ids"]])
+    recall_hnsw_c, recall_ours_c = hnsw.recall_at_k(hc_ids, exc_rows), hnsw.recall_at_k(oc_rows, exc_rows)
     client.reset()
     lat, lat_text = np.array(lat) * 1e3, np.array(lat_text) * 1e3
     return {"config": "cfg1", "workload": f"{rows} x 384 metric embeddings in the semantic store, 1 query, top-{k}",
@@ -194,6 +233,10 @@ def cfg1(rows=10_000):
             "store_search_metadata_ms_p50": float(np.percentile(lat_text, 50)),
             "index_rows_per_s": rows / t_index,
             "cpu_oracle_ms_per_query": float(np.median(t_cpu) * 1e3), "cpu_oracle_qps": float(1 / np.median(t_cpu)), "cpu_threads": threads,
+            "hnsw_port_ms_per_query": t_hnsw * 1e3, "hnsw_port_qps": 1 / t_hnsw, "hnsw_port_threads": 1,
+            "hnsw_port_build_rows_per_s": rows / t_graph, "hnsw_params": "cosine M=16 ef_construction=200 ef_search=100",
+            "recall_at_k_hnsw_vs_exact": recall_hnsw, "recall_at_k_ours_vs_exact": recall_ours, "recall_queries": nq,
+            "recall_at_k_hnsw_vs_exact_clustered": recall_hnsw_c, "recall_at_k_ours_vs_exact_clustered": recall_ours_c,
             "parity_vs_oracle": bool(parity), "store_result_shape_ok": bool(shape_ok)}
 
 
