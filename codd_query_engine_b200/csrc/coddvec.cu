@@ -113,12 +113,14 @@ struct QueryCtx {
     DevBuf<uint32_t> d_mask;
     cv::MmaScratch mma;  // K3 scratch (bf16 queries, per-CTA lists)
     unsigned int* d_counter = nullptr;
+    uint64_t* d_heads = nullptr;  // K2 heads bound: [4 queries][kHeadSlots], zero between launches (self-resetting)
     PinBuf<float> h_q;
     PinBuf<uint64_t> h_out;
     struct Plan { cv::ScanFn fn; int grid; size_t smem; };
     std::unordered_map<int, Plan> plans;  // (qb, pred, k) -> launch plan
     ~QueryCtx() {
         if (d_counter) cudaFree(d_counter);
+        if (d_heads) cudaFree(d_heads);
         if (mma.p) cudaFree(mma.p);
         if (busy) cudaEventDestroy(busy);
         if (t0) cudaEventDestroy(t0);
@@ -208,6 +210,8 @@ int acquire_ctx(cv_index* idx, QueryCtx** out) {
     // stream-ordered: the context's streams are non-blocking, so a NULL-stream cudaMemset would not be
     // ordered before the first kernel that uses the counter; `busy` carries the dependency to any stream
     CV_CUDA(cudaMemsetAsync(c->d_counter, 0, 64 * sizeof(unsigned int), c->stream));
+    CV_CUDA(cudaMalloc(&c->d_heads, 4 * cv::kHeadSlots * sizeof(uint64_t)));
+    CV_CUDA(cudaMemsetAsync(c->d_heads, 0, 4 * cv::kHeadSlots * sizeof(uint64_t), c->stream));
     CV_CUDA(cudaEventRecord(c->busy, c->stream));
     {
         std::lock_guard<std::mutex> g(idx->ctx_mu);
@@ -251,7 +255,7 @@ int plan_scan(cv_index* idx, QueryCtx* c, int qb, int k, bool pred, ScanLaunch* 
     const int nch = (idx->C + 15) / 16;
     ScanFn fn = pick_scan(nch, qb, pred);
     if (!fn) return fail(CV_ERR_UNSUPPORTED, "scan path: no kernel for dim=%d with %d queries per pass", idx->D, qb);
-    size_t smem = (static_cast<size_t>(kSelCap) + static_cast<size_t>(kScanWarps) * qb * k) * sizeof(uint64_t);
+    size_t smem = (static_cast<size_t>(kSelCap) + static_cast<size_t>(kScanWarps) * qb * scan_list_cap(k)) * sizeof(uint64_t);
     if (scan_is_wide(nch)) smem += static_cast<size_t>(idx->Dp) * sizeof(float);  // the normalised query
     CV_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     int occ = 0;
@@ -367,6 +371,7 @@ int enqueue_query(cv_index* idx, QueryCtx* c, cudaStream_t stream, const float* 
             a.row_offset = static_cast<uint32_t>(idx->cfg.row_offset);
             a.partial = c->d_partial.p;
             a.counter = c->d_counter;
+            a.heads = c->d_heads;
             a.out = d_out + static_cast<size_t>(done) * k;
             if (exchange) a.px = *px; else a.px.world = 0;
             a.seq = seq;

@@ -90,6 +90,62 @@ __device__ __forceinline__ uint64_t warp_list_insert(uint64_t* list, int k, uint
 }
 
 // ---------------------------------------------------------------------------------------------
+// K2's per-(warp, query) candidate store: an UNSORTED buffer of cap = scan_list_cap(k) keys.  A candidate
+// that beats the register threshold is appended by one lane (a single shared-memory store); only when the
+// buffer is full does the warp prune it to its k best -- every lane ranks its cap/32 keys against all cap
+// keys (keys are unique: they carry the row id), keys of rank < k are scattered to buf[rank], so the survivors
+// come out sorted and buf[k-1] is the new threshold.  Compared with keeping the list sorted on every insert
+// (warp_list_insert) the fill phase costs one store per row instead of a ballot/shift pass, which is what
+// dominates when a warp sees only a few hundred rows (predicate scans, small shards) and k is large.
+// The threshold is stale between prunes, so somewhat more candidates are appended; each costs ~one store.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int scan_list_cap(int k) { return k <= 32 ? 64 : (k <= 64 ? 128 : 256); }
+
+template <int CAP>
+__device__ __forceinline__ uint64_t warp_prune_impl(uint64_t* buf, int k, int lane) {
+    constexpr int PER = CAP / 32;
+    uint64_t mine[PER];
+    int rank[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        mine[j] = buf[j * 32 + lane];
+        rank[j] = 0;
+    }
+    const ulonglong2* pairs = reinterpret_cast<const ulonglong2*>(buf);  // warp-uniform address: broadcast reads
+#pragma unroll 4
+    for (int i = 0; i < CAP / 2; ++i) {
+        const ulonglong2 o = pairs[i];
+#pragma unroll
+        for (int j = 0; j < PER; ++j) rank[j] += (o.x > mine[j] ? 1 : 0) + (o.y > mine[j] ? 1 : 0);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < PER; ++j)
+        if (rank[j] < k) buf[rank[j]] = mine[j];
+    __syncwarp();
+    return buf[k - 1];
+}
+
+// All 32 lanes call; buf holds exactly `cap` distinct non-zero keys.  Returns the k-th best.
+__device__ __forceinline__ uint64_t warp_prune(uint64_t* buf, int cap, int k, int lane) {
+    if (cap == 64) return warp_prune_impl<64>(buf, k, lane);
+    if (cap == 128) return warp_prune_impl<128>(buf, k, lane);
+    return warp_prune_impl<256>(buf, k, lane);
+}
+
+// Append `key` (warp-uniform) to the buffer; prune when it fills.  cnt is warp-uniform.  Returns true when a
+// prune happened, in which case `kth` holds the new k-th best key of this buffer.
+__device__ __forceinline__ bool warp_buf_append(uint64_t* buf, int cap, int k, uint64_t key, int lane, int& cnt,
+                                                uint64_t& kth) {
+    if (lane == 0) buf[cnt] = key;
+    if (++cnt < cap) return false;
+    __syncwarp();
+    kth = warp_prune(buf, cap, k, lane);
+    cnt = k;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Block-wide bitonic sort (descending) of n = power of two u64 keys in shared memory.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void block_bitonic_desc(uint64_t* buf, int n) {

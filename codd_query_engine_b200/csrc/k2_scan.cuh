@@ -40,6 +40,7 @@ struct ScanArgs {
     uint64_t* partial;      // [QB][gridDim.x][k]
     unsigned int* counter;  // self-resetting "CTAs done" counter
     uint64_t* out;          // [QB][k] final keys (desc, 0 padded)
+    uint64_t* heads;        // [QB][kHeadSlots] group maxima of the keys warps have kept (self-resetting, see heads_bound_key)
     PeerExchange px;        // world > 1: the last CTA also exchanges + merges across GPUs (fused)
     uint64_t seq;           // exchange sequence number of this batch
     int q_base;             // global query index of this launch's query 0
@@ -86,6 +87,40 @@ __device__ __forceinline__ int reduce16_index(int hl) {
     return idx;
 }
 
+// ---- cross-CTA "heads" bound ------------------------------------------------------------------------
+// Every warp of the grid folds the best key it has kept for query b into heads[b][its slot] (atomicMax; a
+// slot pools the warps with the same global warp index mod kHeadSlots).  The slot maxima are keys of
+// DISTINCT rows, so the k-th largest of them is a lower bound on the k-th best key of the whole scan -- and a
+// tight one: it tracks the rows ALL warps have seen, where a warp's own k-th best only reflects its few
+// hundred rows.  One warp per CTA recomputes it at iteration counts 1, 2, 4, 8, ... (the warps take turns) and
+// publishes it in shared memory; every warp folds it into its register threshold.  With it a warp stops
+// buffering candidates after its first handful of rows, which is what makes large k cheap when the rows per
+// warp are few (predicate scans, small shards).  Only the score half of the keys is ranked (a bit-wise binary
+// search over 32 bits: 4 ballots per bit), the returned key has row bits 0, i.e. it is <= the exact bound.
+constexpr int kHeadSlots = 128;  // >= kMaxK
+
+__device__ __forceinline__ uint64_t heads_bound_key(const uint64_t* heads, int k, int lane) {
+    uint32_t h[kHeadSlots / 32];
+#pragma unroll
+    for (int j = 0; j < kHeadSlots / 32; ++j)
+        h[j] = static_cast<uint32_t>(__ldcg(reinterpret_cast<const unsigned long long*>(heads) + j * 32 + lane) >> 32);
+    uint32_t t = 0u;
+#pragma unroll 1
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t c = t | (1u << bit);
+        int n = 0;
+#pragma unroll
+        for (int j = 0; j < kHeadSlots / 32; ++j) n += __popc(__ballot_sync(kFullMask, h[j] >= c));
+        if (n >= k) t = c;
+    }
+    return static_cast<uint64_t>(t) << 32;
+}
+
+// it = process() calls this warp has finished; true on the calls where this warp refreshes the CTA's bound
+__device__ __forceinline__ bool heads_refresh_turn(uint32_t it, int warp) {
+    return (it & (it - 1u)) == 0u && ((31 - __clz(it)) & (kScanWarps - 1)) == warp;
+}
+
 __device__ __forceinline__ uint64_t block_max_u64(uint64_t v, uint64_t* s_red) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -100,23 +135,41 @@ __device__ __forceinline__ uint64_t block_max_u64(uint64_t v, uint64_t* s_red) {
     return r;
 }
 
-// Shared by K2 and K3: the CTA has k-lists of `nlists` producers per query in shared memory
-// (lists[(p * QBn + b) * k + j]); merge -> publish -> last CTA merges all CTAs.
-// selbuf: kSelCap keys of shared scratch.
+// The CTA has candidate buffers of `nlists` producers per query in shared memory
+// (lists[(p * QBn + b) * len + j], any order, 0 = empty).  Tail of the launch:
+//   1. every CTA selects its k best above the heads bound B (by now within ~2x of the exact k-th best, so only a
+//      handful of keys in the whole grid survive) and appends the survivors COMPACTLY to partial[b][...]
+//      (one atomicAdd on counter[1 + b] per CTA reserves the range);
+//   2. the last CTA to finish (threadfence + counter[0]) selects the k best of the survivors -- a few hundred
+//      keys instead of gridDim.x * k -- runs the fused cross-GPU exchange if there is one, writes out[b][0..k)
+//      and resets the counters and the heads for the next launch.
+// partial: [QBn][gridDim.x * k] keys.  selbuf: kSelCap keys of shared scratch.
 template <int QBn>
-__device__ __forceinline__ void publish_and_final_merge(const uint64_t* lists, int nlists, int k,
+__device__ __forceinline__ void publish_and_final_merge(const uint64_t* lists, int nlists, int len, int k,
                                                         uint64_t* partial, unsigned int* counter,
                                                         uint64_t* out, uint64_t* selbuf, int* s_cnt,
                                                         uint64_t* s_red, const PeerExchange& px, uint64_t seq,
-                                                        int q_base) {
+                                                        int q_base, uint64_t* heads) {
     __shared__ int s_last;
+    __shared__ unsigned int s_pos;
+    __shared__ unsigned long long s_hb;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t stride = static_cast<size_t>(gridDim.x) * k;
+    (void)s_red;
     __syncthreads();
 #pragma unroll 1
     for (int b = 0; b < QBn; ++b) {
-        auto src = [&](int i) { int p = i / k, j = i - p * k; return lists[(p * QBn + b) * k + j]; };
-        block_select_topk(src, nlists * k, k, 0ull, selbuf, s_cnt);
-        for (int j = threadIdx.x; j < k; j += blockDim.x)
-            partial[(static_cast<size_t>(b) * gridDim.x + blockIdx.x) * k + j] = selbuf[j];
+        if (warp == 0) {
+            const uint64_t hb = heads_bound_key(heads + b * kHeadSlots, k, lane);
+            if (lane == 0) s_hb = hb;
+        }
+        __syncthreads();
+        auto src = [&](int i) { int p = i / len, j = i - p * len; return lists[(p * QBn + b) * len + j]; };
+        block_select_topk(src, nlists * len, k, s_hb, selbuf, s_cnt);
+        const int nsurv = __syncthreads_count(static_cast<int>(threadIdx.x) < k && selbuf[threadIdx.x] != 0ull);
+        if (threadIdx.x == 0) s_pos = nsurv ? atomicAdd(counter + 1 + b, static_cast<unsigned int>(nsurv)) : 0u;
+        __syncthreads();
+        if (static_cast<int>(threadIdx.x) < nsurv) partial[b * stride + s_pos + threadIdx.x] = selbuf[threadIdx.x];
         __syncthreads();
     }
     __threadfence();
@@ -125,23 +178,23 @@ __device__ __forceinline__ void publish_and_final_merge(const uint64_t* lists, i
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    const int G = gridDim.x;
 #pragma unroll 1
     for (int b = 0; b < QBn; ++b) {
-        const uint64_t* pb = partial + static_cast<size_t>(b) * G * k;
-        uint64_t tau = 0;
-        for (int c = threadIdx.x; c < G; c += blockDim.x) {
-            uint64_t kth = __ldcg(pb + static_cast<size_t>(c) * k + (k - 1));
-            tau = kth > tau ? kth : tau;
+        const uint64_t* pb = partial + b * stride;
+        const int m = static_cast<int>(__ldcg(counter + 1 + b));
+        if (warp == 0) {
+            const uint64_t hb = heads_bound_key(heads + b * kHeadSlots, k, lane);
+            if (lane == 0) s_hb = hb;
         }
-        tau = block_max_u64(tau, s_red);
+        __syncthreads();
         auto src = [&](int i) { return __ldcg(pb + i); };
-        block_select_topk<8>(src, G * k, k, tau, selbuf, s_cnt);
+        block_select_topk<8>(src, m, k, s_hb, selbuf, s_cnt);
         if (px.world > 1) exchange_and_merge(px, seq, q_base + b, selbuf, k, selbuf, s_cnt);  // fused NVLink exchange
         for (int j = threadIdx.x; j < k; j += blockDim.x) out[static_cast<size_t>(b) * k + j] = selbuf[j];
         __syncthreads();
     }
-    if (threadIdx.x == 0) *counter = 0u;
+    if (threadIdx.x <= QBn) counter[threadIdx.x] = 0u;
+    for (int i = threadIdx.x; i < QBn * kHeadSlots; i += blockDim.x) heads[i] = 0ull;  // every other CTA is done
 }
 
 // rows-per-half per iteration: keep ~12 (<= 16) independent 16-byte loads per lane in flight.
@@ -151,8 +204,20 @@ __host__ __device__ constexpr int scan_rph(int nch, int qb) {
     return r < 1 ? 1 : r;
 }
 
+// Row slots handed to process(): the unfiltered scan counts rows in int64 (-1 = empty slot); the predicate
+// scan carries LOCAL rows as u32 (keys hold 32-bit global rows, so a shard never exceeds 2^32 - 1 rows) with
+// 0xFFFFFFFF = empty, which halves the index arithmetic of its row-gather.
+template <bool PRED> struct ScanRow { using type = int64_t; };
+template <> struct ScanRow<true> { using type = uint32_t; };
+__device__ __forceinline__ bool row_valid(int64_t r) { return r >= 0; }
+__device__ __forceinline__ bool row_valid(uint32_t r) { return r != 0xFFFFFFFFu; }
+
+constexpr int kRingCap = 256;  // per-warp ring of eligible rows (predicate scan): >= 128 + max slots - 1
+
 template <int NCH, int QB, bool PRED>
 __global__ void __launch_bounds__(kScanThreads, (NCH * QB <= 6) ? 2 : 1) k_scan_topk(ScanArgs a) {
+    using row_t = typename ScanRow<PRED>::type;
+    constexpr row_t kEmptyRow = static_cast<row_t>(-1);
     constexpr int RPH = scan_rph(NCH, QB);
     constexpr int S = 2 * RPH;   // row slots per warp iteration
     constexpr int V = RPH * QB;  // partial sums per half-warp
@@ -160,11 +225,12 @@ __global__ void __launch_bounds__(kScanThreads, (NCH * QB <= 6) ? 2 : 1) k_scan_
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* selbuf = reinterpret_cast<uint64_t*>(smem_raw);                 // kSelCap keys (32 KB)
-    uint64_t* lists = selbuf + kSelCap;                                       // [warps][QB][k]
+    uint64_t* lists = selbuf + kSelCap;                                       // [warps][QB][cap] candidate buffers
     float* sq = reinterpret_cast<float*>(smem_raw);                           // prologue alias: [QB][D]
     __shared__ float s_norm[QB];
     __shared__ int s_cnt;
     __shared__ uint64_t s_red[kScanWarps];
+    __shared__ unsigned long long s_bound[QB];  // heads bound of each query, refreshed by the warps in turn
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -172,11 +238,13 @@ __global__ void __launch_bounds__(kScanThreads, (NCH * QB <= 6) ? 2 : 1) k_scan_
     const int half = lane >> 4;
     const int hl = lane & 15;
     const int k = a.k;
+    const int cap = scan_list_cap(k);
     const int C = a.C;
 
     // ---- prologue: normalise the queries exactly like the oracle (fp64 norm, fp32 divide) ----
     for (int i = tid; i < QB * a.D; i += kScanThreads) sq[i] = a.q[i];
-    for (int i = tid; i < kScanWarps * QB * k; i += kScanThreads) lists[i] = 0ull;
+    for (int i = tid; i < kScanWarps * QB * cap; i += kScanThreads) lists[i] = 0ull;
+    if (tid < QB) s_bound[tid] = 0ull;
     __syncthreads();
     if (warp < QB) {
         float nrm = 1.0f;
@@ -211,29 +279,35 @@ __global__ void __launch_bounds__(kScanThreads, (NCH * QB <= 6) ? 2 : 1) k_scan_
     const int my_b = my_idx % QB;
     const int my_slot = 2 * (my_idx / QB) + half;
     const bool owner = (hl & ((16 / V) - 1)) == 0;
-    uint64_t* my_lists = lists + static_cast<size_t>(warp) * QB * k;
-    uint64_t thr = 0ull;  // k-th best key of my query's list (0 while not full)
+    uint64_t* my_lists = lists + static_cast<size_t>(warp) * QB * cap;
+    uint64_t thr = 0ull;  // k-th best key of my query's buffer at its last prune (0 before the first)
+    int cnt[QB];          // keys in each query's buffer (warp-uniform)
+    uint64_t best[QB];    // best key this warp has kept per query (what it has folded into the heads)
+#pragma unroll
+    for (int b = 0; b < QB; ++b) { cnt[b] = 0; best[b] = 0ull; }
+    uint32_t it = 0;      // process() calls finished
 
     const int64_t gw = static_cast<int64_t>(blockIdx.x) * kScanWarps + warp;
     const int64_t nw = static_cast<int64_t>(gridDim.x) * kScanWarps;
+    const int head_slot = static_cast<int>(gw % kHeadSlots);
 
-    auto process = [&](const int64_t (&rows)[S]) {
-        // rows[s] < 0 => empty slot.  Issue every load first.
+    auto process = [&](const row_t (&rows)[S]) {
+        // rows[s] == kEmptyRow => empty slot.  Issue every load first.
         uint4 ld[RPH][NCH];
 #pragma unroll
         for (int i = 0; i < RPH; ++i) {
-            const int64_t r = half ? rows[2 * i + 1] : rows[2 * i];  // (select, not a dynamic index)
+            const row_t r = half ? rows[2 * i + 1] : rows[2 * i];  // (select, not a dynamic index)
+            const uint4* rp = a.E + static_cast<size_t>(r) * C + hl;
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
-                const int ci = hl + 16 * c;
-                if (r >= 0 && ci < C) ld[i][c] = ldg_stream(a.E + r * C + ci);
+                if (row_valid(r) && hl + 16 * c < C) ld[i][c] = ldg_stream(rp + 16 * c);
                 else ld[i][c] = make_uint4(0u, 0u, 0u, 0u);
             }
         }
-        int64_t my_row = -1;
+        row_t my_row = kEmptyRow;
 #pragma unroll
         for (int s = 0; s < S; ++s) my_row = (s == my_slot) ? rows[s] : my_row;
-        const float sc = (my_row >= 0) ? __ldg(a.scale + my_row) : 0.0f;
+        const float sc = row_valid(my_row) ? __ldg(a.scale + my_row) : 0.0f;
 
         float acc[V];
 #pragma unroll
@@ -259,19 +333,40 @@ __global__ void __launch_bounds__(kScanThreads, (NCH * QB <= 6) ? 2 : 1) k_scan_
         const float dot = reduce16<V>(acc, hl);
         const float score = dot * sc;
         const uint64_t key = pack_key(score, a.row_offset + static_cast<uint32_t>(my_row));
-        const bool cand = owner && my_row >= 0 && key > thr;
+        {
+            const uint64_t sb = s_bound[my_b];
+            thr = sb > thr ? sb : thr;
+        }
+        const bool cand = owner && row_valid(my_row) && key > thr;
         unsigned int pending = __ballot_sync(kFullMask, cand);
         while (pending) {
             const int src = __ffs(pending) - 1;
             pending &= pending - 1;
             const uint64_t ck = shfl_u64(key, src);
             const int cb = __shfl_sync(kFullMask, my_b, src);
-            const uint64_t kth = warp_list_insert(my_lists + cb * k, k, ck, lane);
-            if (cb == my_b) thr = kth;
+#pragma unroll
+            for (int b = 0; b < QB; ++b) {
+                if (b == cb) {  // warp-uniform
+                    uint64_t kth;
+                    if (warp_buf_append(my_lists + b * cap, cap, k, ck, lane, cnt[b], kth) && b == my_b && kth > thr) thr = kth;
+                    if (ck > best[b]) {
+                        best[b] = ck;
+                        if (lane == 0) atomicMax(reinterpret_cast<unsigned long long*>(a.heads) + b * kHeadSlots + head_slot, ck);
+                    }
+                }
+            }
+        }
+        ++it;
+        if (heads_refresh_turn(it, warp)) {  // warp-uniform, rare
+#pragma unroll 1
+            for (int b = 0; b < QB; ++b) {
+                const uint64_t hb = heads_bound_key(a.heads + b * kHeadSlots, k, lane);
+                if (lane == 0 && hb != 0ull) atomicMax(&s_bound[b], hb);
+            }
         }
     };
 
-    if (!PRED) {
+    if constexpr (!PRED) {
         const int64_t groups = (a.n + S - 1) / S;
         for (int64_t g = gw; g < groups; g += nw) {
             int64_t rows[S];
@@ -283,59 +378,76 @@ __global__ void __launch_bounds__(kScanThreads, (NCH * QB <= 6) ? 2 : 1) k_scan_
             process(rows);
         }
     } else {
-        // 128 rows per warp step: build the eligibility words, then consume set bits S at a time.  The
-        // codes / mask words of the NEXT step are loaded before the current step's rows are processed, so
-        // their latency overlaps the row loads instead of preceding them.
+        // 128 rows per warp step.  Lane l tests rows base + 4l .. base + 4l + 3 (one 16-byte load per code
+        // column, one mask word), four ballots turn that into eligibility words, and the eligible rows are
+        // COMPACTED into a per-warp ring in shared memory (position = running tail + popc of the lower lanes).
+        // The ring is consumed S rows at a time, so every process() call runs with all its slots filled no
+        // matter how the selected rows fall into 128-row steps; only the final flush is partial.  The codes /
+        // mask word of the NEXT step are loaded before this step's rows are processed, so their latency
+        // overlaps the row loads.
+        __shared__ __align__(16) uint32_t s_ring[kScanWarps][kRingCap];
+        uint32_t* ring = s_ring[warp];
+        const uint32_t lt_mask = (1u << lane) - 1u;
         const int64_t blocks = (a.n + 127) / 128;
         const int64_t nwords = (a.n + 31) / 32;
         const bool use_ns = a.ns_code != kAny, use_label = a.label_code != kAny;
-        uint32_t nsv[4], lbv[4], mkv[4];
+        uint4 nsv, lbv;
+        uint32_t mkv;
         auto fetch = [&](int64_t blk) {
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-                const int64_t r = blk * 128 + 32 * w + lane;
-                const bool in = blk < blocks && r < a.n;
-                nsv[w] = (in && use_ns) ? __ldg(a.ns + r) : a.ns_code;
-                lbv[w] = (in && use_label) ? __ldg(a.label + r) : a.label_code;
-                const int64_t wi = blk * 4 + w;
-                mkv[w] = (a.mask && blk < blocks && wi < nwords) ? __ldg(a.mask + wi) : (a.mask ? 0u : 0xFFFFFFFFu);
-            }
+            const int64_t r0 = blk * 128 + 4 * lane;  // 16-byte aligned; the arrays are mapped in 16-byte multiples
+            const bool in = blk < blocks && r0 < a.n;
+            nsv = (in && use_ns) ? __ldg(reinterpret_cast<const uint4*>(a.ns + r0)) : make_uint4(a.ns_code, a.ns_code, a.ns_code, a.ns_code);
+            lbv = (in && use_label) ? __ldg(reinterpret_cast<const uint4*>(a.label + r0))
+                                    : make_uint4(a.label_code, a.label_code, a.label_code, a.label_code);
+            const int64_t wi = blk * 4 + (lane >> 3);
+            mkv = a.mask ? ((blk < blocks && wi < nwords) ? __ldg(a.mask + wi) : 0u) : 0xFFFFFFFFu;
         };
+        auto consume = [&](uint32_t at, uint32_t avail) {  // avail >= S: full group
+            row_t rows[S];
+#pragma unroll
+            for (int s = 0; s < S; ++s) rows[s] = (static_cast<uint32_t>(s) < avail) ? ring[(at + s) & (kRingCap - 1)] : kEmptyRow;
+            process(rows);
+        };
+        uint32_t head = 0, tail = 0;  // warp-uniform; head stays a multiple of S
         fetch(gw);
         for (int64_t blk = gw; blk < blocks; blk += nw) {
-            const int64_t base = blk * 128;
-            uint32_t words[4];
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-                const int64_t r = base + 32 * w + lane;
-                const bool ok = r < a.n && nsv[w] == a.ns_code && lbv[w] == a.label_code;
-                words[w] = __ballot_sync(kFullMask, ok) & mkv[w];
-            }
+            const uint32_t base = static_cast<uint32_t>(blk * 128) + 4u * lane;
+            const uint32_t mbits = mkv >> ((4 * lane) & 31);
+            const int64_t rem = a.n - (blk * 128 + 4 * lane);  // rows of this lane's quad that exist
+            const int left = rem >= 4 ? 4 : (rem > 0 ? static_cast<int>(rem) : 0);
+            const bool ok0 = left > 0 && nsv.x == a.ns_code && lbv.x == a.label_code && (mbits & 1u);
+            const bool ok1 = left > 1 && nsv.y == a.ns_code && lbv.y == a.label_code && (mbits & 2u);
+            const bool ok2 = left > 2 && nsv.z == a.ns_code && lbv.z == a.label_code && (mbits & 4u);
+            const bool ok3 = left > 3 && nsv.w == a.ns_code && lbv.w == a.label_code && (mbits & 8u);
+            const uint32_t w0 = __ballot_sync(kFullMask, ok0), w1 = __ballot_sync(kFullMask, ok1);
+            const uint32_t w2 = __ballot_sync(kFullMask, ok2), w3 = __ballot_sync(kFullMask, ok3);
             fetch(blk + nw);
-            int remaining = __popc(words[0]) + __popc(words[1]) + __popc(words[2]) + __popc(words[3]);
-            while (remaining > 0) {
-                int64_t rows[S];
-#pragma unroll
-                for (int s = 0; s < S; ++s) {
-                    int64_t r = -1;
-#pragma unroll
-                    for (int w = 0; w < 4; ++w) {
-                        if (r < 0 && words[w]) {
-                            const int bit = __ffs(words[w]) - 1;
-                            words[w] &= words[w] - 1;
-                            r = base + 32 * w + bit;
-                        }
-                    }
-                    rows[s] = r;
-                }
-                remaining -= S;
-                process(rows);
+            uint32_t t = tail;
+            if (ok0) ring[(t + __popc(w0 & lt_mask)) & (kRingCap - 1)] = base;
+            t += __popc(w0);
+            if (ok1) ring[(t + __popc(w1 & lt_mask)) & (kRingCap - 1)] = base + 1;
+            t += __popc(w1);
+            if (ok2) ring[(t + __popc(w2 & lt_mask)) & (kRingCap - 1)] = base + 2;
+            t += __popc(w2);
+            if (ok3) ring[(t + __popc(w3 & lt_mask)) & (kRingCap - 1)] = base + 3;
+            tail = t + __popc(w3);
+            __syncwarp();
+            while (tail - head >= static_cast<uint32_t>(S)) {
+                consume(head, S);
+                head += S;
             }
+            __syncwarp();  // ring slots read above may be overwritten by the next step's appends
         }
+        if (tail != head) consume(head, tail - head);
     }
 
-    publish_and_final_merge<QB>(lists, kScanWarps, k, a.partial, a.counter, a.out, selbuf, &s_cnt, s_red, a.px, a.seq,
-                                a.q_base);
+    // slots past each buffer's count hold keys a prune dropped: blank them before the CTA merge reads all `cap`
+    __syncwarp();
+#pragma unroll
+    for (int b = 0; b < QB; ++b)
+        for (int i = cnt[b] + lane; i < cap; i += 32) my_lists[b * cap + i] = 0ull;
+    publish_and_final_merge<QB>(lists, kScanWarps, cap, k, a.partial, a.counter, a.out, selbuf, &s_cnt, s_red, a.px, a.seq,
+                                a.q_base, a.heads);
 }
 
 // K2 for long rows (Dp > 1024, up to CV_MAX_DIM): the query no longer fits the register file, so it
@@ -348,16 +460,19 @@ template <bool PRED>
 __global__ void __launch_bounds__(kScanThreads, 2) k_scan_topk_wide(ScanArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* selbuf = reinterpret_cast<uint64_t*>(smem_raw);          // kSelCap keys
-    uint64_t* lists = selbuf + kSelCap;                                // [warps][k]
-    float* sq = reinterpret_cast<float*>(lists + kScanWarps * a.k);    // [C * 8] normalised query, zero padded
+    uint64_t* lists = selbuf + kSelCap;                                // [warps][cap] candidate buffers
+    const int cap = scan_list_cap(a.k);
+    float* sq = reinterpret_cast<float*>(lists + kScanWarps * cap);    // [C * 8] normalised query, zero padded
     __shared__ float s_norm;
     __shared__ int s_cnt;
     __shared__ uint64_t s_red[kScanWarps];
+    __shared__ unsigned long long s_bound;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int k = a.k, C = a.C;
+    if (tid == 0) s_bound = 0ull;
     for (int i = tid; i < C * 8; i += kScanThreads) sq[i] = i < a.D ? a.q[i] : 0.0f;
-    for (int i = tid; i < kScanWarps * k; i += kScanThreads) lists[i] = 0ull;
+    for (int i = tid; i < kScanWarps * cap; i += kScanThreads) lists[i] = 0ull;
     __syncthreads();
     if (warp == 0) {
         float nrm = 1.0f;
@@ -378,10 +493,13 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_topk_wide(ScanArgs a) 
     for (int i = tid; i < a.D; i += kScanThreads) sq[i] = __fdiv_rn(sq[i], s_norm);
     __syncthreads();
 
-    uint64_t* my_list = lists + static_cast<size_t>(warp) * k;
-    uint64_t thr = 0ull;
+    uint64_t* my_list = lists + static_cast<size_t>(warp) * cap;
+    uint64_t thr = 0ull, best = 0ull;
+    int cnt = 0;
+    uint32_t it = 0;
     const int64_t gw = static_cast<int64_t>(blockIdx.x) * kScanWarps + warp;
     const int64_t nw = static_cast<int64_t>(gridDim.x) * kScanWarps;
+    const int head_slot = static_cast<int>(gw % kHeadSlots);
     const float4* sq4 = reinterpret_cast<const float4*>(sq);
 
     auto process = [&](const int64_t (&rows)[kWideRows]) {
@@ -407,6 +525,10 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_topk_wide(ScanArgs a) 
                 acc[r] += s0 + s1;
             }
         }
+        {
+            const uint64_t sb = s_bound;
+            thr = sb > thr ? sb : thr;
+        }
 #pragma unroll
         for (int r = 0; r < kWideRows; ++r) {
 #pragma unroll
@@ -414,8 +536,20 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_topk_wide(ScanArgs a) 
             if (rows[r] >= 0) {  // warp-uniform
                 const float score = acc[r] * __ldg(a.scale + rows[r]);
                 const uint64_t key = pack_key(score, a.row_offset + static_cast<uint32_t>(rows[r]));
-                if (key > thr) thr = warp_list_insert(my_list, k, key, lane);
+                if (key > thr) {
+                    uint64_t kth;
+                    if (warp_buf_append(my_list, cap, k, key, lane, cnt, kth) && kth > thr) thr = kth;
+                    if (key > best) {
+                        best = key;
+                        if (lane == 0) atomicMax(reinterpret_cast<unsigned long long*>(a.heads) + head_slot, key);
+                    }
+                }
             }
+        }
+        ++it;
+        if (heads_refresh_turn(it, warp)) {
+            const uint64_t hb = heads_bound_key(a.heads, k, lane);
+            if (lane == 0 && hb != 0ull) atomicMax(&s_bound, hb);
         }
     };
 
@@ -470,8 +604,10 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_topk_wide(ScanArgs a) 
             }
         }
     }
-    publish_and_final_merge<1>(lists, kScanWarps, k, a.partial, a.counter, a.out, selbuf, &s_cnt, s_red, a.px, a.seq,
-                               a.q_base);
+    __syncwarp();
+    for (int i = cnt + lane; i < cap; i += 32) my_list[i] = 0ull;
+    publish_and_final_merge<1>(lists, kScanWarps, cap, k, a.partial, a.counter, a.out, selbuf, &s_cnt, s_red, a.px, a.seq,
+                               a.q_base, a.heads);
 }
 
 using ScanFn = void (*)(ScanArgs);

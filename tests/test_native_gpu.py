@@ -171,6 +171,38 @@ def test_scan_predicates(native):
     idx.close()
 
 
+@pytest.mark.parametrize("D", [64, 384, 768, 1024])
+def test_scan_predicate_ragged_sizes_and_selectivities(native, D):
+    """The predicate scan compacts eligible rows 128 at a time into per-warp rings: sizes around the 128-row
+    step / 4-row quad boundaries, selectivities from all rows to a single row, namespace + label + bitmask."""
+    rng = np.random.default_rng(D)
+    k = 7
+    for n in (1, 3, 4, 5, 127, 128, 129, 131, 255, 1000, 4099, 70001):
+        x = rng.standard_normal((n, D)).astype(np.float32)
+        ns = rng.integers(1, 3, n).astype(np.uint32)
+        label = rng.integers(1, 4, n).astype(np.uint32)
+        q = rng.standard_normal((1, D)).astype(np.float32)
+        idx = make_index(native, x, ns=ns, label=label)
+        stored, scale, _, _ = stored_of(idx)
+        full = oracle_full_scores(stored, scale, q)
+        for sel in (1.0, 0.5, 0.03):
+            bits = rng.random(n) < sel
+            bits[rng.integers(0, n)] = True
+            words = np.packbits(np.concatenate([bits, np.zeros((-n) % 32, bool)]), bitorder="little").view(np.uint32)
+            s, r, c = idx.query(q, k, mask=words, path=native.PATH_SCAN)
+            check_topk(s, r, c, full, bits, k, tol=2e-6)
+            s, r, c = idx.query(q, k, mask=words, ns_code=1, label_code=2, path=native.PATH_SCAN)
+            check_topk(s, r, c, full, bits & (ns == 1) & (label == 2), k, tol=2e-6)
+        s, r, c = idx.query(q, k, ns_code=2, path=native.PATH_SCAN)
+        check_topk(s, r, c, full, ns == 2, k, tol=2e-6)
+        one = np.zeros(n, bool)
+        one[n - 1] = True  # only the very last row
+        words = np.packbits(np.concatenate([one, np.zeros((-n) % 32, bool)]), bitorder="little").view(np.uint32)
+        s, r, c = idx.query(q, k, mask=words, path=native.PATH_SCAN)
+        assert c[0] == 1 and r[0, 0] == n - 1
+        idx.close()
+
+
 def test_ip_metric(native):
     rng = np.random.default_rng(13)
     n, D, k = 20000, 384, 10
