@@ -291,23 +291,39 @@ __global__ void __launch_bounds__(kScanThreads, (NCH * QB <= 6) ? 2 : 1) k_scan_
     const int64_t nw = static_cast<int64_t>(gridDim.x) * kScanWarps;
     const int head_slot = static_cast<int>(gw % kHeadSlots);
 
-    auto process = [&](const row_t (&rows)[S]) {
+    // fast = std::true_type: the S slots are the consecutive rows rows[0] .. rows[0] + S - 1, all of them exist and
+    // every lane's chunks exist (C == 16 * NCH); gp = address of this lane's first chunk of the row in slot `half`.
+    // No validity tests, no row selects: the loads are base + constant offsets.  That is every group of the
+    // unfiltered scan except a ragged last one.
+    // (FAST is a literal at every call site and the lambda is inlined, so the unused side folds away; a generic
+    // lambda with `if constexpr` here crashes nvcc 12.9's front end.)
+    auto process = [&](const bool FAST, const row_t (&rows)[S], const uint4* gp) {
         // rows[s] == kEmptyRow => empty slot.  Issue every load first.
         uint4 ld[RPH][NCH];
-#pragma unroll
-        for (int i = 0; i < RPH; ++i) {
-            const row_t r = half ? rows[2 * i + 1] : rows[2 * i];  // (select, not a dynamic index)
-            const uint4* rp = a.E + static_cast<size_t>(r) * C + hl;
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-                if (row_valid(r) && hl + 16 * c < C) ld[i][c] = ldg_stream(rp + 16 * c);
-                else ld[i][c] = make_uint4(0u, 0u, 0u, 0u);
-            }
-        }
         row_t my_row = kEmptyRow;
+        if (FAST) {
 #pragma unroll
-        for (int s = 0; s < S; ++s) my_row = (s == my_slot) ? rows[s] : my_row;
-        const float sc = row_valid(my_row) ? __ldg(a.scale + my_row) : 0.0f;
+            for (int i = 0; i < RPH; ++i) {
+                const uint4* rp = gp + static_cast<size_t>(2 * i) * C;
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) ld[i][c] = ldg_stream(rp + 16 * c);
+            }
+            my_row = rows[0] + my_slot;
+        } else {
+#pragma unroll
+            for (int i = 0; i < RPH; ++i) {
+                const row_t r = half ? rows[2 * i + 1] : rows[2 * i];  // (select, not a dynamic index)
+                const uint4* rp = a.E + static_cast<size_t>(r) * C + hl;
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    if (row_valid(r) && hl + 16 * c < C) ld[i][c] = ldg_stream(rp + 16 * c);
+                    else ld[i][c] = make_uint4(0u, 0u, 0u, 0u);
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < S; ++s) my_row = (s == my_slot) ? rows[s] : my_row;
+        }
+        const float sc = (FAST || row_valid(my_row)) ? __ldg(a.scale + my_row) : 0.0f;
 
         float acc[V];
 #pragma unroll
@@ -337,7 +353,7 @@ __global__ void __launch_bounds__(kScanThreads, (NCH * QB <= 6) ? 2 : 1) k_scan_
             const uint64_t sb = s_bound[my_b];
             thr = sb > thr ? sb : thr;
         }
-        const bool cand = owner && row_valid(my_row) && key > thr;
+        const bool cand = owner && (FAST || row_valid(my_row)) && key > thr;
         unsigned int pending = __ballot_sync(kFullMask, cand);
         while (pending) {
             const int src = __ffs(pending) - 1;
@@ -368,14 +384,27 @@ __global__ void __launch_bounds__(kScanThreads, (NCH * QB <= 6) ? 2 : 1) k_scan_
 
     if constexpr (!PRED) {
         const int64_t groups = (a.n + S - 1) / S;
-        for (int64_t g = gw; g < groups; g += nw) {
+        const int64_t full_groups = a.n / S;
+        auto ragged = [&](int64_t g) {
             int64_t rows[S];
 #pragma unroll
             for (int s = 0; s < S; ++s) {
                 int64_t r = g * S + s;
                 rows[s] = r < a.n ? r : -1;
             }
-            process(rows);
+            process(false, rows, nullptr);
+        };
+        if (C == 16 * NCH) {
+            const uint4* gp = a.E + static_cast<size_t>(gw * S + half) * C + hl;
+            const size_t gstride = static_cast<size_t>(nw) * S * C;
+            for (int64_t g = gw; g < full_groups; g += nw, gp += gstride) {
+                int64_t rows[S];
+                rows[0] = g * S;
+                process(true, rows, gp);
+            }
+            if (full_groups < groups && full_groups % nw == gw) ragged(full_groups);
+        } else {
+            for (int64_t g = gw; g < groups; g += nw) ragged(g);
         }
     } else {
         // 128 rows per warp step.  Lane l tests rows base + 4l .. base + 4l + 3 (one 16-byte load per code
@@ -406,7 +435,7 @@ __global__ void __launch_bounds__(kScanThreads, (NCH * QB <= 6) ? 2 : 1) k_scan_
             row_t rows[S];
 #pragma unroll
             for (int s = 0; s < S; ++s) rows[s] = (static_cast<uint32_t>(s) < avail) ? ring[(at + s) & (kRingCap - 1)] : kEmptyRow;
-            process(rows);
+            process(false, rows, nullptr);
         };
         uint32_t head = 0, tail = 0;  // warp-uniform; head stays a multiple of S
         fetch(gw);
