@@ -22,6 +22,8 @@ namespace cv {
 constexpr int kScanThreads = 256;
 constexpr int kScanWarps = kScanThreads / 32;
 
+constexpr int kInlineQ = 1024;
+
 struct ScanArgs {
     const uint4* E;         // [n][C] 16-byte chunks (bf16 x 8)
     const float* scale;     // [n]
@@ -40,10 +42,16 @@ struct ScanArgs {
     uint64_t* partial;      // [QB][gridDim.x][k]
     unsigned int* counter;  // self-resetting "CTAs done" counter
     uint64_t* out;          // [QB][k] final keys (desc, 0 padded)
+    int q_inline;           // 1: the (single) query travels in qinline[] with the launch instead of behind q
+    uint64_t* done_flag;    // nullptr, or host-mapped word the last CTA sets to done_value once out[] is written
+    uint64_t done_value;    // (cv_query's low-latency completion: the host polls it instead of a stream sync)
     uint64_t* heads;        // [QB][kHeadSlots] group maxima of the keys warps have kept (self-resetting, see heads_bound_key)
     PeerExchange px;        // world > 1: the last CTA also exchanges + merges across GPUs (fused)
     uint64_t seq;           // exchange sequence number of this batch
     int q_base;             // global query index of this launch's query 0
+    // Low-latency path of cv_query (one interactive query, D <= kInlineQ): the query rides in the kernel
+    // parameters, so no copy-engine operation precedes the launch and no CTA reads it over PCIe.
+    float qinline[kInlineQ];
 };
 
 // Transposing butterfly over the 16 lanes of a half-warp.  On return the lane holds the full sum of
@@ -137,19 +145,22 @@ __device__ __forceinline__ uint64_t block_max_u64(uint64_t v, uint64_t* s_red) {
 
 // The CTA has candidate buffers of `nlists` producers per query in shared memory
 // (lists[(p * QBn + b) * len + j], any order, 0 = empty).  Tail of the launch:
-//   1. every CTA selects its k best above the heads bound B (by now within ~2x of the exact k-th best, so only a
-//      handful of keys in the whole grid survive) and appends the survivors COMPACTLY to partial[b][...]
-//      (one atomicAdd on counter[1 + b] per CTA reserves the range);
+//   1. every CTA selects its k best above the heads bound it already holds in shared memory (bound[b], from its
+//      last refresh; on a long scan within ~2x of the exact k-th best, so only a handful of keys in the whole
+//      grid survive) and appends the survivors COMPACTLY to partial[b][...] (one atomicAdd on counter[1 + b]
+//      per CTA reserves the range);
 //   2. the last CTA to finish (threadfence + counter[0]) selects the k best of the survivors -- a few hundred
-//      keys instead of gridDim.x * k -- runs the fused cross-GPU exchange if there is one, writes out[b][0..k)
-//      and resets the counters and the heads for the next launch.
+//      keys instead of gridDim.x * k; if the bounds were still loose (short scans) it first recomputes the
+//      final heads bound so that one small sort suffices -- runs the fused cross-GPU exchange if there is
+//      one, writes out[b][0..k) and resets the counters and the heads for the next launch.
 // partial: [QBn][gridDim.x * k] keys.  selbuf: kSelCap keys of shared scratch.
 template <int QBn>
 __device__ __forceinline__ void publish_and_final_merge(const uint64_t* lists, int nlists, int len, int k,
                                                         uint64_t* partial, unsigned int* counter,
                                                         uint64_t* out, uint64_t* selbuf, int* s_cnt,
                                                         uint64_t* s_red, const PeerExchange& px, uint64_t seq,
-                                                        int q_base, uint64_t* heads) {
+                                                        int q_base, uint64_t* heads, const unsigned long long* bound,
+                                                        uint64_t* done_flag = nullptr, uint64_t done_value = 0) {
     __shared__ int s_last;
     __shared__ unsigned int s_pos;
     __shared__ unsigned long long s_hb;
@@ -159,13 +170,8 @@ __device__ __forceinline__ void publish_and_final_merge(const uint64_t* lists, i
     __syncthreads();
 #pragma unroll 1
     for (int b = 0; b < QBn; ++b) {
-        if (warp == 0) {
-            const uint64_t hb = heads_bound_key(heads + b * kHeadSlots, k, lane);
-            if (lane == 0) s_hb = hb;
-        }
-        __syncthreads();
         auto src = [&](int i) { int p = i / len, j = i - p * len; return lists[(p * QBn + b) * len + j]; };
-        block_select_topk(src, nlists * len, k, s_hb, selbuf, s_cnt);
+        block_select_topk(src, nlists * len, k, bound[b], selbuf, s_cnt);
         const int nsurv = __syncthreads_count(static_cast<int>(threadIdx.x) < k && selbuf[threadIdx.x] != 0ull);
         if (threadIdx.x == 0) s_pos = nsurv ? atomicAdd(counter + 1 + b, static_cast<unsigned int>(nsurv)) : 0u;
         __syncthreads();
@@ -183,7 +189,7 @@ __device__ __forceinline__ void publish_and_final_merge(const uint64_t* lists, i
         const uint64_t* pb = partial + b * stride;
         const int m = static_cast<int>(__ldcg(counter + 1 + b));
         if (warp == 0) {
-            const uint64_t hb = heads_bound_key(heads + b * kHeadSlots, k, lane);
+            const uint64_t hb = m > 512 ? heads_bound_key(heads + b * kHeadSlots, k, lane) : 0ull;
             if (lane == 0) s_hb = hb;
         }
         __syncthreads();
@@ -195,6 +201,11 @@ __device__ __forceinline__ void publish_and_final_merge(const uint64_t* lists, i
     }
     if (threadIdx.x <= QBn) counter[threadIdx.x] = 0u;
     for (int i = threadIdx.x; i < QBn * kHeadSlots; i += blockDim.x) heads[i] = 0ull;  // every other CTA is done
+    if (done_flag) {  // out[] (host-mapped in this mode) is complete: tell the polling host thread
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) st_release_sys(done_flag, done_value);
+    }
 }
 
 // rows-per-half per iteration: keep ~12 (<= 16) independent 16-byte loads per lane in flight.
@@ -242,7 +253,11 @@ __global__ void __launch_bounds__(kScanThreads, (NCH * QB <= 6) ? 2 : 1) k_scan_
     const int C = a.C;
 
     // ---- prologue: normalise the queries exactly like the oracle (fp64 norm, fp32 divide) ----
-    for (int i = tid; i < QB * a.D; i += kScanThreads) sq[i] = a.q[i];
+    if (QB == 1 && a.q_inline) {
+        for (int i = tid; i < a.D; i += kScanThreads) sq[i] = a.qinline[i];
+    } else {
+        for (int i = tid; i < QB * a.D; i += kScanThreads) sq[i] = a.q[i];
+    }
     for (int i = tid; i < kScanWarps * QB * cap; i += kScanThreads) lists[i] = 0ull;
     if (tid < QB) s_bound[tid] = 0ull;
     __syncthreads();
@@ -297,7 +312,9 @@ __global__ void __launch_bounds__(kScanThreads, (NCH * QB <= 6) ? 2 : 1) k_scan_
     // unfiltered scan except a ragged last one.
     // (FAST is a literal at every call site and the lambda is inlined, so the unused side folds away; a generic
     // lambda with `if constexpr` here crashes nvcc 12.9's front end.)
-    auto process = [&](const bool FAST, const row_t (&rows)[S], const uint4* gp) {
+    // DENSE (predicate scan, full groups out of the ring): arbitrary rows, but every slot is filled and every
+    // lane's chunks exist, so the gather needs no validity tests either.
+    auto process = [&](const bool FAST, const bool DENSE, const row_t (&rows)[S], const uint4* gp) {
         // rows[s] == kEmptyRow => empty slot.  Issue every load first.
         uint4 ld[RPH][NCH];
         row_t my_row = kEmptyRow;
@@ -316,14 +333,14 @@ __global__ void __launch_bounds__(kScanThreads, (NCH * QB <= 6) ? 2 : 1) k_scan_
                 const uint4* rp = a.E + static_cast<size_t>(r) * C + hl;
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) {
-                    if (row_valid(r) && hl + 16 * c < C) ld[i][c] = ldg_stream(rp + 16 * c);
+                    if (DENSE || (row_valid(r) && hl + 16 * c < C)) ld[i][c] = ldg_stream(rp + 16 * c);
                     else ld[i][c] = make_uint4(0u, 0u, 0u, 0u);
                 }
             }
 #pragma unroll
             for (int s = 0; s < S; ++s) my_row = (s == my_slot) ? rows[s] : my_row;
         }
-        const float sc = (FAST || row_valid(my_row)) ? __ldg(a.scale + my_row) : 0.0f;
+        const float sc = (FAST || DENSE || row_valid(my_row)) ? __ldg(a.scale + my_row) : 0.0f;
 
         float acc[V];
 #pragma unroll
@@ -353,7 +370,7 @@ __global__ void __launch_bounds__(kScanThreads, (NCH * QB <= 6) ? 2 : 1) k_scan_
             const uint64_t sb = s_bound[my_b];
             thr = sb > thr ? sb : thr;
         }
-        const bool cand = owner && (FAST || row_valid(my_row)) && key > thr;
+        const bool cand = owner && (FAST || DENSE || row_valid(my_row)) && key > thr;
         unsigned int pending = __ballot_sync(kFullMask, cand);
         while (pending) {
             const int src = __ffs(pending) - 1;
@@ -392,7 +409,7 @@ __global__ void __launch_bounds__(kScanThreads, (NCH * QB <= 6) ? 2 : 1) k_scan_
                 int64_t r = g * S + s;
                 rows[s] = r < a.n ? r : -1;
             }
-            process(false, rows, nullptr);
+            process(false, false, rows, nullptr);
         };
         if (C == 16 * NCH) {
             const uint4* gp = a.E + static_cast<size_t>(gw * S + half) * C + hl;
@@ -400,7 +417,7 @@ __global__ void __launch_bounds__(kScanThreads, (NCH * QB <= 6) ? 2 : 1) k_scan_
             for (int64_t g = gw; g < full_groups; g += nw, gp += gstride) {
                 int64_t rows[S];
                 rows[0] = g * S;
-                process(true, rows, gp);
+                process(true, false, rows, gp);
             }
             if (full_groups < groups && full_groups % nw == gw) ragged(full_groups);
         } else {
@@ -431,11 +448,13 @@ __global__ void __launch_bounds__(kScanThreads, (NCH * QB <= 6) ? 2 : 1) k_scan_
             const int64_t wi = blk * 4 + (lane >> 3);
             mkv = a.mask ? ((blk < blocks && wi < nwords) ? __ldg(a.mask + wi) : 0u) : 0xFFFFFFFFu;
         };
+        const bool fullc = C == 16 * NCH;
         auto consume = [&](uint32_t at, uint32_t avail) {  // avail >= S: full group
             row_t rows[S];
 #pragma unroll
             for (int s = 0; s < S; ++s) rows[s] = (static_cast<uint32_t>(s) < avail) ? ring[(at + s) & (kRingCap - 1)] : kEmptyRow;
-            process(false, rows, nullptr);
+            if (fullc && avail >= static_cast<uint32_t>(S)) process(false, true, rows, nullptr);
+            else process(false, false, rows, nullptr);
         };
         uint32_t head = 0, tail = 0;  // warp-uniform; head stays a multiple of S
         fetch(gw);
@@ -476,7 +495,7 @@ __global__ void __launch_bounds__(kScanThreads, (NCH * QB <= 6) ? 2 : 1) k_scan_
     for (int b = 0; b < QB; ++b)
         for (int i = cnt[b] + lane; i < cap; i += 32) my_lists[b * cap + i] = 0ull;
     publish_and_final_merge<QB>(lists, kScanWarps, cap, k, a.partial, a.counter, a.out, selbuf, &s_cnt, s_red, a.px, a.seq,
-                                a.q_base, a.heads);
+                                a.q_base, a.heads, s_bound, a.done_flag, a.done_value);
 }
 
 // K2 for long rows (Dp > 1024, up to CV_MAX_DIM): the query no longer fits the register file, so it
@@ -636,7 +655,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_topk_wide(ScanArgs a) 
     __syncwarp();
     for (int i = cnt + lane; i < cap; i += 32) my_list[i] = 0ull;
     publish_and_final_merge<1>(lists, kScanWarps, cap, k, a.partial, a.counter, a.out, selbuf, &s_cnt, s_red, a.px, a.seq,
-                               a.q_base, a.heads);
+                               a.q_base, a.heads, &s_bound, a.done_flag, a.done_value);
 }
 
 using ScanFn = void (*)(ScanArgs);
