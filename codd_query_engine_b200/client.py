@@ -353,11 +353,14 @@ class Collection:
             if self._metric == native.METRIC_COSINE:
                 np.clip(scores, -1.0, 1.0, out=scores)
             res = empty()
+            hits = rows.tolist()
+            counts = counts.tolist()
+            dist = (np.float32(1.0) - scores).tolist() if "distances" in include else None  # fp32 arithmetic, like Chroma
             for b in range(B):
-                hit = [int(r) for r in rows[b, : int(counts[b])]]
+                hit = hits[b][: counts[b]]
                 res["ids"][b] = [self._ids[r] for r in hit]
-                if "distances" in include:
-                    res["distances"][b] = [float(np.float32(1.0) - s) for s in scores[b, : len(hit)]]
+                if dist is not None:
+                    res["distances"][b] = dist[b][: len(hit)]
                 if "metadatas" in include:
                     res["metadatas"][b] = [dict(self._metadatas[r]) if self._metadatas[r] is not None else None for r in hit]
                 if "documents" in include:
