@@ -97,7 +97,10 @@ struct PinBuf {
 };
 
 // AUTO path: batches up to this size take the fp32-exact K2 scan, larger ones the tensor-core K3.
+// (Rows up to 384 elements: two queries still fit one K2 pass at HBM speed -- 0.140 ms against K3's 0.151 ms on
+// 1M x 384 -- four do not, the FMA work doubles again and the pass drops to 3.4 TB/s.)
 constexpr int kAutoScanMaxBatch = 1;
+constexpr int kAutoScanMaxBatchShortRows = 2;
 
 // Per-query scratch.  A context is used by one query batch at a time; `busy` orders reuse on a
 // different stream without blocking the host.
@@ -309,7 +312,8 @@ int enqueue_query(cv_index* idx, QueryCtx* c, cudaStream_t stream, const float* 
     if (path == CV_PATH_AUTO) {
         // B = 1: fp32-exact K2 scan.  Batches: K3 on the tensor cores, except where K3 has no fast top-k
         // (k > 64 keeps lists in shared / global memory) and the batch is small enough for a few K2 passes.
-        const bool scan = B <= std::min(max_qb, kAutoScanMaxBatch) || !mma_supported(idx->Dp) ||
+        const int auto_scan = nch <= 3 ? kAutoScanMaxBatchShortRows : kAutoScanMaxBatch;
+        const bool scan = B <= std::min(max_qb, auto_scan) || !mma_supported(idx->Dp) ||
                           (k > 64 && max_qb > 0 && B <= 4 * max_qb);
         path = scan ? CV_PATH_SCAN : CV_PATH_MMA;
     }
@@ -392,8 +396,8 @@ int enqueue_query(cv_index* idx, QueryCtx* c, cudaStream_t stream, const float* 
             a.done_flag = (done_flag && last_launch) ? done_flag->flag : nullptr;
             a.done_value = done_flag ? done_flag->value : 0;
             a.q_inline = 0;
-            if (done_flag && done_flag->h_q && qb == 1 && idx->D <= kInlineQ && !scan_is_wide(nch)) {
-                memcpy(a.qinline, done_flag->h_q + static_cast<size_t>(done) * idx->D, sizeof(float) * idx->D);
+            if (done_flag && done_flag->h_q && qb * idx->D <= kInlineQ && !scan_is_wide(nch)) {
+                memcpy(a.qinline, done_flag->h_q + static_cast<size_t>(done) * idx->D, sizeof(float) * qb * idx->D);
                 a.q_inline = 1;
             }
             if (a.done_flag) done_flag->armed = true;
@@ -811,8 +815,8 @@ int cv_query(cv_index* idx, const float* q, const cv_query_params* p, float* out
 
 namespace cv {
 cudaError_t launch_merge_keys(const uint64_t* in, int G, int b_stride, int k_in, int k_out, uint64_t* out, int nq,
-                              cudaStream_t stream) {
-    k_merge_keys<<<nq, 256, 0, stream>>>(in, G, b_stride, k_in, k_out, out);
+                              cudaStream_t stream, const uint32_t* bound32) {
+    k_merge_keys<<<nq, 256, 0, stream>>>(in, G, b_stride, k_in, k_out, out, bound32);
     return cudaGetLastError();
 }
 }  // namespace cv
@@ -867,7 +871,7 @@ int cv_merge_keys_device(int32_t device, const uint64_t* d_keys_in, int32_t G, i
         return fail(CV_ERR_INVALID, "bad merge shape G=%d B=%d k_in=%d k_out=%d", G, B, k_in, k_out);
     DeviceGuard dg(device);
     if (!dg.ok) return fail(CV_ERR_CUDA, "cudaSetDevice(%d) failed", device);
-    k_merge_keys<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_keys_in, G, B, k_in, k_out, d_keys_out);
+    k_merge_keys<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_keys_in, G, B, k_in, k_out, d_keys_out, nullptr);
     CV_CUDA(cudaGetLastError());
     return CV_OK;
 }

@@ -42,7 +42,7 @@ struct ScanArgs {
     uint64_t* partial;      // [QB][gridDim.x][k]
     unsigned int* counter;  // self-resetting "CTAs done" counter
     uint64_t* out;          // [QB][k] final keys (desc, 0 padded)
-    int q_inline;           // 1: the (single) query travels in qinline[] with the launch instead of behind q
+    int q_inline;           // 1: the queries of this pass travel in qinline[] with the launch instead of behind q
     uint64_t* done_flag;    // nullptr, or host-mapped word the last CTA sets to done_value once out[] is written
     uint64_t done_value;    // (cv_query's low-latency completion: the host polls it instead of a stream sync)
     uint64_t* heads;        // [QB][kHeadSlots] group maxima of the keys warps have kept (self-resetting, see heads_bound_key)
@@ -253,8 +253,8 @@ __global__ void __launch_bounds__(kScanThreads, (NCH * QB <= 6) ? 2 : 1) k_scan_
     const int C = a.C;
 
     // ---- prologue: normalise the queries exactly like the oracle (fp64 norm, fp32 divide) ----
-    if (QB == 1 && a.q_inline) {
-        for (int i = tid; i < a.D; i += kScanThreads) sq[i] = a.qinline[i];
+    if (a.q_inline) {  // QB * D <= kInlineQ
+        for (int i = tid; i < QB * a.D; i += kScanThreads) sq[i] = a.qinline[i];
     } else {
         for (int i = tid; i < QB * a.D; i += kScanThreads) sq[i] = a.q[i];
     }
@@ -676,8 +676,10 @@ inline ScanFn scan_fn(bool pred) {
 // K4 `merge_topk`: one CTA per query merges G lists of k_in keys ([G][B][k_in]) into k_out keys.
 // Used (a) after the NCCL all-gather of per-GPU top-k and (b) to combine query-tile passes.
 #ifdef CV_MAIN_TU
+// bound32 (nullable): per query, the high word of a key known to be <= the k_out-th best (K3's shared threshold:
+// the largest k-th best any CTA reached) -- drops almost every candidate before it touches shared memory.
 __global__ void __launch_bounds__(256) k_merge_keys(const uint64_t* in, int G, int B, int k_in, int k_out,
-                                                    uint64_t* out) {
+                                                    uint64_t* out, const uint32_t* bound32) {
     __shared__ __align__(16) uint64_t selbuf[kSelCap];
     __shared__ int s_cnt;
     __shared__ uint64_t s_red[8];
@@ -689,6 +691,10 @@ __global__ void __launch_bounds__(256) k_merge_keys(const uint64_t* in, int G, i
             tau = kth > tau ? kth : tau;
         }
         tau = block_max_u64(tau, s_red);
+    }
+    if (bound32) {
+        const uint64_t bk = static_cast<uint64_t>(bound32[b]) << 32;
+        tau = bk > tau ? bk : tau;
     }
     auto src = [&](int i) { int g = i / k_in, j = i - g * k_in; return in[(static_cast<size_t>(g) * B + b) * k_in + j]; };
     block_select_topk<8>(src, G * k_in, k_out, tau, selbuf, &s_cnt);

@@ -815,7 +815,8 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         MMA_CUDA(cudaLaunchKernelEx(&cfg, kernel, tq, te, a));
-        MMA_CUDA(launch_merge_keys(lists, P, Bpad, m.k, m.k, m.out + static_cast<size_t>(done) * m.k, Bs, m.stream));
+        MMA_CUDA(launch_merge_keys(lists, P, Bpad, m.k, m.k, m.out + static_cast<size_t>(done) * m.k, Bs, m.stream,
+                                   P > 1 && !m.dump ? gthr : nullptr));
         if (launches) launches->fetch_add(3);
         done += Bs;
         if (done < m.B) MMA_CUDA(cudaStreamSynchronize(m.stream));  // scratch is reused by the next slice

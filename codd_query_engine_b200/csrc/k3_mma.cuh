@@ -41,6 +41,6 @@ std::string& mma_error();
 
 // K4 launcher (kernel lives in coddvec.cu): merge G lists [G][b_stride][k_in] -> out[nq][k_out]
 cudaError_t launch_merge_keys(const uint64_t* in, int G, int b_stride, int k_in, int k_out, uint64_t* out, int nq,
-                              cudaStream_t stream);
+                              cudaStream_t stream, const uint32_t* bound32 = nullptr);
 
 }  // namespace cv
