@@ -28,6 +28,8 @@ class MicroBatcher:
         if max_batch < 1:
             raise ValueError("max_batch must be >= 1")
         self.collection = collection
+        # the collection's own entry point below any CODDVEC_MICROBATCH routing (a batch of one must not come back here)
+        self._search = getattr(collection, "_query_direct", collection.query)
         self.max_batch = int(max_batch)
         self.max_wait = float(max_wait_ms) / 1e3
         self._cv = threading.Condition()
@@ -51,7 +53,7 @@ class MicroBatcher:
             if emb.ndim == 1:
                 emb = emb[None, :]
         if emb.shape[0] != 1:  # already a batch: nothing to coalesce
-            return self.collection.query(query_embeddings=emb, n_results=n_results, where=where, include=include)
+            return self._search(query_embeddings=emb, n_results=n_results, where=where, include=include)
         group = (int(n_results), json.dumps(where, sort_keys=True, default=str), None if include is None else tuple(include))
         fut: Future = Future()
         with self._cv:
@@ -91,7 +93,7 @@ class MicroBatcher:
                 return
             kw = batch[0][2]
             try:
-                res = self.collection.query(query_embeddings=np.stack([b[1] for b in batch]), **kw)
+                res = self._search(query_embeddings=np.stack([b[1] for b in batch]), **kw)
                 self.batches += 1
                 self.requests += len(batch)
                 for i, (_, _, _, fut) in enumerate(batch):

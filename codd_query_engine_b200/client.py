@@ -311,7 +311,33 @@ class Collection:
 
     def query(self, query_embeddings=None, query_texts=None, n_results: int = 10, where=None, include=None,
               **_ignored) -> dict:
-        """Exact cosine / inner-product top-k.  Results per query ascend by distance = 1 - score."""
+        """Exact cosine / inner-product top-k.  Results per query ascend by distance = 1 - score.
+
+        With CODDVEC_MICROBATCH=1 in the environment, single-query calls from concurrent threads are coalesced
+        into one batched search (batching.MicroBatcher; CODDVEC_MICROBATCH_MAX, CODDVEC_MICROBATCH_WAIT_MS) --
+        the zero-edit way to put a multi-threaded service on the tensor path."""
+        if os.environ.get("CODDVEC_MICROBATCH", "0") not in ("", "0"):
+            if query_texts is not None:
+                single = isinstance(query_texts, str) or len(query_texts) == 1
+            else:
+                shape = np.shape(query_embeddings) if query_embeddings is not None else ()
+                single = len(shape) == 1 or (len(shape) == 2 and shape[0] == 1)
+            if single:
+                return self._microbatcher().query(query_embeddings=query_embeddings, query_texts=query_texts,
+                                                  n_results=n_results, where=where, include=include)
+        return self._query_direct(query_embeddings=query_embeddings, query_texts=query_texts, n_results=n_results,
+                                  where=where, include=include)
+
+    def _microbatcher(self):
+        with self._lock:
+            if getattr(self, "_batcher", None) is None:
+                from .batching import MicroBatcher
+
+                self._batcher = MicroBatcher(self, max_batch=int(os.environ.get("CODDVEC_MICROBATCH_MAX", "256")),
+                                             max_wait_ms=float(os.environ.get("CODDVEC_MICROBATCH_WAIT_MS", "0.2")))
+            return self._batcher
+
+    def _query_direct(self, query_embeddings=None, query_texts=None, n_results: int = 10, where=None, include=None) -> dict:
         include = self._check_include(include, _QUERY_INCLUDE)
         if (query_embeddings is None) == (query_texts is None):
             raise ValueError("You must provide exactly one of query_embeddings or query_texts")
@@ -439,6 +465,9 @@ class Collection:
         return None if self._index is None else self._index.stats()
 
     def close(self) -> None:
+        batcher, self._batcher = getattr(self, "_batcher", None), None
+        if batcher is not None:
+            batcher.close()  # outside the lock: its worker takes it to search
         with self._lock:
             if self._index is not None:
                 self._index.close()
@@ -470,10 +499,12 @@ class Client:
     as separate ``chromadb.HttpClient(host, port)`` objects pointed at one server do (the reference
     service builds a fresh client per request: codd_service/.../metrics_controller.py:168)."""
 
-    def __init__(self, endpoint: Any = "ephemeral", device: int = 0,
+    def __init__(self, endpoint: Any = "ephemeral", device: Optional[int] = None,
                  embedding_function: Optional[Callable] = None, **_ignored):
         self._reg = _registry(endpoint)
-        self._device = int(device)
+        # service wiring without source edits (SURVEY.md section 8f rank 4): CODDVEC_DEVICE picks the CUDA ordinal
+        # for clients built by unmodified callers (chromadb.HttpClient(host, port) has no such argument)
+        self._device = int(os.environ.get("CODDVEC_DEVICE", "0")) if device is None else int(device)
         self._embedding_function = embedding_function
         self.endpoint = endpoint
         self._path = endpoint[1] if isinstance(endpoint, tuple) and endpoint and endpoint[0] == "path" else None
@@ -581,7 +612,14 @@ def HttpClient(host: str = "localhost", port: int = 8000, **kwargs) -> Client:  
     kwargs.pop("ssl", None)
     kwargs.pop("headers", None)
     kwargs.pop("settings", None)
-    return Client(("http", str(host), int(port)), **kwargs)
+    client = Client(("http", str(host), int(port)), **kwargs)
+    # CODDVEC_SNAPSHOT_DIR: the stand-in for the Chroma server's volume (docker-compose.yml:8-9).  The first
+    # client of an endpoint loads the snapshots found there; `client.persist()` with no argument writes them back.
+    snap = os.environ.get("CODDVEC_SNAPSHOT_DIR")
+    if snap:
+        client._path = os.path.join(os.path.abspath(snap), f"{host}_{int(port)}")
+        client._load_snapshots()
+    return client
 
 
 def PersistentClient(path: str = "./chroma", **kwargs) -> Client:  # noqa: N802

@@ -69,3 +69,53 @@ def test_text_queries_and_errors(coll):
     mb.close()
     with pytest.raises(RuntimeError):
         mb.query(query_embeddings=x[0], n_results=3)
+
+
+def test_env_wiring_routes_single_queries_through_a_batcher(coll, monkeypatch):
+    """CODDVEC_MICROBATCH=1: unmodified callers (store.py:314-316 calls collection.query with one text) are
+    coalesced without source edits; answers equal the direct search; batches of one do not recurse."""
+    coll, x = coll
+    want = [coll.query(query_embeddings=x[i], n_results=4) for i in range(12)]
+    monkeypatch.setenv("CODDVEC_MICROBATCH", "1")
+    monkeypatch.setenv("CODDVEC_MICROBATCH_WAIT_MS", "30")
+    got = [None] * 12
+    start = threading.Barrier(12)
+
+    def worker(i):
+        start.wait()
+        got[i] = coll.query(query_embeddings=x[i], n_results=4)
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(12)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert coll._batcher is not None and coll._batcher.requests == 12 and coll._batcher.batches < 12
+    for g, w in zip(got, want):
+        assert g["ids"] == w["ids"]
+        assert np.allclose(g["distances"][0], w["distances"][0], atol=1e-3)
+    lone = coll.query(query_embeddings=x[100], n_results=3)   # a batch of one
+    assert lone["ids"][0][0] == "100"
+    multi = coll.query(query_embeddings=x[:5], n_results=3)    # already a batch: straight through
+    assert [r[0] for r in multi["ids"]] == ["0", "1", "2", "3", "4"]
+    assert coll._batcher.requests == 13
+
+
+def test_env_device_and_snapshot_dir(monkeypatch, tmp_path):
+    monkeypatch.setattr(client_mod, "NativeIndex", OracleIndex)
+    monkeypatch.setenv("CODDVEC_DEVICE", "0")
+    monkeypatch.setenv("CODDVEC_SNAPSHOT_DIR", str(tmp_path))
+    c = client_mod.HttpClient(host="snap-host", port=8123)
+    assert c._device == 0
+    coll = c.get_or_create_collection("metrics_semantic_metadata", metadata={"hnsw:space": "cosine"})
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((50, 384)).astype(np.float32)
+    coll.upsert(ids=[f"ns#m{i}" for i in range(50)], embeddings=x, documents=[f"doc {i}" for i in range(50)])
+    before = coll.query(query_embeddings=x[7], n_results=3)
+    root = c.persist()
+    assert root.startswith(str(tmp_path))
+    c.reset()                                                   # "service restart"
+    c2 = client_mod.HttpClient(host="snap-host", port=8123)
+    again = c2.get_or_create_collection("metrics_semantic_metadata")
+    assert again.count() == 50
+    after = again.query(query_embeddings=x[7], n_results=3)
+    assert after["ids"] == before["ids"] and after["documents"] == before["documents"]
+    c2.reset()
