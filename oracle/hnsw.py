@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import subprocess
 
 import numpy as np
 
@@ -28,8 +29,9 @@ def _lib():
     global _LIB
     if _LIB is None:
         path = os.path.join(_HERE, "liboracle_hnsw.so")
-        if not os.path.exists(path):
-            raise RuntimeError(f"{path} missing: run `make -C oracle`")
+        if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(os.path.join(_HERE, "hnsw.c")):
+            env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+            subprocess.run(["make", "-C", _HERE, "liboracle_hnsw.so"], check=True, capture_output=True, env=env)
         lib = ctypes.CDLL(path)
         lib.hnsw_create.restype = ctypes.c_void_p
         lib.hnsw_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_uint64]
