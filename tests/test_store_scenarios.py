@@ -154,3 +154,61 @@ def test_complete_metric_semantic_metadata_workflow(store):
     assert len(upd) > 0 and upd[0]["metric_name"] == "http.request.duration.p99"
     assert "UPDATED" in upd[0]["description"] and "improved accuracy" in upd[0]["description"]
     assert store.collection.count() == 5
+
+
+# ---- extensions: the bulk calls must be indistinguishable from the per-item ones
+def _catalogue(n):
+    kinds = [("cpu", "CPU utilization percentage of the host"), ("memory", "Memory usage in bytes"),
+             ("http.latency", "HTTP request latency in milliseconds"), ("disk.io", "Disk read and write operations"),
+             ("queue.depth", "Messages waiting in the queue")]
+    return [{"metric_name": f"{kinds[i % 5][0]}.{i}", "description": f"{kinds[i % 5][1]} (series {i})",
+             "category": "system" if i % 2 else "application", "type": "gauge"} for i in range(n)]
+
+
+def test_bulk_index_equals_per_item_index(chromadb_client, request):
+    one = MetricsSemanticMetadataStore(chromadb_client, collection_name=f"one_{request.node.name}")
+    bulk = MetricsSemanticMetadataStore(chromadb_client, collection_name=f"bulk_{request.node.name}")
+    items = _catalogue(2300)                                       # three upsert chunks of <= 1000
+    ids_one = [one.index_metadata("prod", md) for md in items[:300]]
+    ids_bulk = bulk.index_metadata_bulk("prod", items)
+    assert ids_bulk[:300] == ids_one and len(ids_bulk) == 2300 and bulk.collection.count() == 2300
+    for md in items[300:]:
+        one.index_metadata("prod", md)
+    for q in ("CPU utilization", "request latency milliseconds", "queue messages"):
+        a, b = one.search_metadata(q, n_results=7), bulk.search_metadata(q, n_results=7)
+        assert [h["metric_name"] for h in a] == [h["metric_name"] for h in b]
+        assert all(abs(x["similarity_score"] - y["similarity_score"]) < 1e-6 for x, y in zip(a, b))
+    assert bulk.metric_exists("prod", "cpu.0") and not bulk.metric_exists("prod", "nope")
+
+
+def test_bulk_index_validates_everything_before_writing(store):
+    bad = _catalogue(5) + [{"metric_name": "bad name with spaces", "description": "x"}]
+    with pytest.raises(Exception) as exc:
+        store.index_metadata_bulk("prod", bad)
+    assert "ValidationError" in type(exc.value).__name__
+    assert store.collection.count() == 0
+    with pytest.raises(KeyError):
+        store.index_metadata_bulk("prod", [{"description": "no name"}])
+    # a repeated id keeps the LAST entry, as successive index_metadata calls would
+    ids = store.index_metadata_bulk("prod", [{"metric_name": "m", "description": "first text about disks"},
+                                             {"metric_name": "m", "description": "CPU utilization percentage"}])
+    assert ids == ["prod#m", "prod#m"] and store.collection.count() == 1
+    assert "CPU" in store.search_metadata("CPU utilization")[0]["description"]
+
+
+def test_batched_search_equals_single_searches(store):
+    store.index_metadata_bulk("prod", _catalogue(400))
+    queries = ["CPU utilization", "", "request latency milliseconds", "   ", "disk read write", "queue messages waiting"]
+    batched = store.search_metadata_batch(queries, n_results=5)
+    assert len(batched) == len(queries) and batched[1] == [] and batched[3] == []
+    for q, got in zip(queries, batched):
+        want = store.search_metadata(q, n_results=5)
+        assert len(got) == len(want)
+        # the batch may run on the tensor path (bf16 queries): same hits up to near-ties, scores within 1e-3
+        assert len({h["metric_name"] for h in got} & {h["metric_name"] for h in want}) >= len(want) - 1
+        for g in got:
+            assert 0.0 <= g["similarity_score"] <= 1.0 + 1e-6 and g["namespace"] == "prod"
+        for g, w in zip(got, want):
+            assert abs(g["similarity_score"] - w["similarity_score"]) < 1e-3
+    with pytest.raises(Exception):
+        store.search_metadata_batch(["x" * 1001])
