@@ -11,9 +11,18 @@
 // 16-byte loads per lane are in flight before any arithmetic.  The query lives in registers
 // (normalised in the CTA prologue, bit-identical to the oracle).  Partial sums of the V = RPH*QB
 // (row, query) pairs of a half-warp are reduced with a transposing butterfly (V/2 + V/4 + ... shuffles
-// instead of 4*V).  Each warp keeps a sorted k-list per query in shared memory behind a register
-// threshold; CTAs merge their warps' lists, publish one k-list per query, and the last CTA to finish
-// merges all CTA lists (threadfence + counter), so a query batch is ONE kernel launch.
+// instead of 4*V).
+//
+// Top-k: a candidate that beats the lane's register threshold is appended to an unsorted per-(warp, query)
+// buffer in shared memory (common.cuh: warp_buf_append / warp_prune).  The threshold is the larger of the
+// buffer's k-th best at its last prune and the cross-CTA HEADS BOUND (heads_bound_key below), which tracks the
+// rows every warp of the grid has seen.  Tail (publish_and_final_merge): each CTA appends its survivors
+// compactly to one global list, the last CTA to finish (threadfence + counter) selects the k best, runs the
+// fused cross-GPU exchange if there is one and writes the result -- a query batch is ONE kernel launch.
+//
+// Three flavours of the inner step (process): FAST -- the unfiltered scan's full groups of consecutive rows (one
+// base pointer, constant offsets, no validity tests); DENSE -- the predicate scan's full groups gathered from the
+// per-warp ring of eligible rows; general -- ragged ends and rows whose last 16-lane chunk group is partial.
 #pragma once
 #include "common.cuh"
 
