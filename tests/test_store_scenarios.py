@@ -204,10 +204,15 @@ def test_batched_search_equals_single_searches(store):
     for q, got in zip(queries, batched):
         want = store.search_metadata(q, n_results=5)
         assert len(got) == len(want)
-        # the batch may run on the tensor path (bf16 queries): same hits up to near-ties, scores within 1e-3
-        assert len({h["metric_name"] for h in got} & {h["metric_name"] for h in want}) >= len(want) - 1
+        # the batch may run on the tensor path (bf16 queries): the catalogue's near-duplicate documents tie within
+        # the 1e-3 tolerance, so the sets may differ -- but only among hits that tie with the single search's k-th
+        if not want:
+            continue
+        kth = want[-1]["similarity_score"]
+        names = {h["metric_name"] for h in want}
         for g in got:
             assert 0.0 <= g["similarity_score"] <= 1.0 + 1e-6 and g["namespace"] == "prod"
+            assert g["metric_name"] in names or g["similarity_score"] >= kth - 1e-3
         for g, w in zip(got, want):
             assert abs(g["similarity_score"] - w["similarity_score"]) < 1e-3
     with pytest.raises(Exception):
