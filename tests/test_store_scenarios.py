@@ -204,16 +204,20 @@ def test_batched_search_equals_single_searches(store):
     for q, got in zip(queries, batched):
         want = store.search_metadata(q, n_results=5)
         assert len(got) == len(want)
-        # the batch may run on the tensor path (bf16 queries): the catalogue's near-duplicate documents tie within
-        # the 1e-3 tolerance, so the sets may differ -- but only among hits that tie with the single search's k-th
+        # the batch may run on the tensor path, which rounds the queries to bf16: |dscore| <= 2^-9 * sum|q_i c_i|.
+        # Dense 384-d embeddings average that down to ~1e-4 (north-star tolerance 1e-3); the hashed bag-of-words
+        # vectors here have a handful of non-zeros, so only the analytic bound 2^-8 (with the rows' own bf16
+        # storage error) holds.  The catalogue's near-duplicate documents tie within it, so the hit sets may
+        # differ -- but only among hits that tie with the single search's k-th
+        tol = 2.0 ** -8
         if not want:
             continue
         kth = want[-1]["similarity_score"]
         names = {h["metric_name"] for h in want}
         for g in got:
             assert 0.0 <= g["similarity_score"] <= 1.0 + 1e-6 and g["namespace"] == "prod"
-            assert g["metric_name"] in names or g["similarity_score"] >= kth - 1e-3
+            assert g["metric_name"] in names or g["similarity_score"] >= kth - tol
         for g, w in zip(got, want):
-            assert abs(g["similarity_score"] - w["similarity_score"]) < 1e-3
+            assert abs(g["similarity_score"] - w["similarity_score"]) < tol
     with pytest.raises(Exception):
         store.search_metadata_batch(["x" * 1001])
