@@ -203,6 +203,50 @@ def test_scan_predicate_ragged_sizes_and_selectivities(native, D):
         idx.close()
 
 
+def _ascending_corpus(n, D, seed):
+    """Rows whose cosine to q grows with the row index: every row a warp meets beats all it has seen, so the
+    per-warp candidate buffers fill and are pruned again and again (on random data the cross-CTA heads bound
+    keeps them nearly empty and the prune path would go untested)."""
+    rng = np.random.default_rng(seed)
+    q = rng.standard_normal(D).astype(np.float32)
+    qh = q / np.linalg.norm(q)
+    u = rng.standard_normal((n, D)).astype(np.float32)
+    u -= (u @ qh)[:, None] * qh[None, :]
+    u /= np.linalg.norm(u, axis=1, keepdims=True)
+    c = np.linspace(0.0, 0.98, n, dtype=np.float32)
+    x = c[:, None] * qh[None, :] + np.sqrt(1.0 - c * c)[:, None] * u
+    return x.astype(np.float32), q
+
+
+@pytest.mark.parametrize("k", [10, 50, 128])
+def test_scan_ascending_scores_exercise_buffer_prunes(native, k):
+    n, D = 1_500_000, 16
+    x, q = _ascending_corpus(n, D, seed=k)
+    ns = (np.arange(n) % 2 + 1).astype(np.uint32)
+    idx = make_index(native, x, ns=ns)
+    stored, scale, _, _ = stored_of(idx)
+    for B in (1, 2, 4):
+        qs = np.stack([q * (1.0 + 0.25 * b) for b in range(B)]).astype(np.float32)   # same direction: all ascending
+        full = oracle_full_scores(stored, scale, qs)
+        s, r, c = idx.query(qs, k, path=native.PATH_SCAN)
+        check_topk(s, r, c, full, None, k, tol=2e-6)
+        if B == 1:
+            s, r, c = idx.query(qs, k, ns_code=2, path=native.PATH_SCAN)            # predicate kernel, 50 % selectivity
+            check_topk(s, r, c, full, ns == 2, k, tol=2e-6)
+    idx.close()
+
+
+def test_scan_wide_ascending_scores_exercise_buffer_prunes(native):
+    n, D, k = 200_000, 1040, 10
+    x, q = _ascending_corpus(n, D, seed=3)
+    idx = make_index(native, x)
+    stored, scale, _, _ = stored_of(idx)
+    full = oracle_full_scores(stored, scale, q[None, :])
+    s, r, c = idx.query(q[None, :], k, path=native.PATH_SCAN)
+    check_topk(s, r, c, full, None, k, tol=4e-6)
+    idx.close()
+
+
 def test_ip_metric(native):
     rng = np.random.default_rng(13)
     n, D, k = 20000, 384, 10
