@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import re
 import zlib
+from functools import lru_cache
 
 import numpy as np
 
@@ -22,6 +23,17 @@ _TOKEN = re.compile(r"[^\W_]+", re.UNICODE)
 _STOP = frozenset(
     "a an and are as at be by for from in is it of on or per the to with all".split()
 )
+
+
+@lru_cache(maxsize=1 << 16)
+def _token_features(tok: str, dim: int, trigram_weight: float) -> tuple:
+    """(slot, weight) pairs of one lower-cased token, in the order they are accumulated.  Metric catalogues repeat
+    the same few thousand words, so the hashing is done once per distinct token."""
+    feats = [(zlib.crc32(("w:" + tok).encode("utf-8")) % dim, 1.0)]
+    if trigram_weight > 0 and len(tok) > 3:
+        marked = f"^{tok}$"
+        feats += [(zlib.crc32(("g:" + marked[i:i + 3]).encode("utf-8")) % dim, trigram_weight) for i in range(len(marked) - 2)]
+    return tuple(feats)
 
 
 class HashedBagOfWordsEmbedding:
@@ -38,15 +50,15 @@ class HashedBagOfWordsEmbedding:
         return zlib.crc32(feature.encode("utf-8")) % dim
 
     def embed_one(self, text: str) -> np.ndarray:
-        v = np.zeros(self.dim, dtype=np.float64)
+        acc: dict[int, float] = {}
         for tok in _TOKEN.findall(text.lower()):
             if tok in _STOP:
                 continue
-            v[self._slot("w:" + tok, self.dim)] += 1.0
-            if self.trigram_weight > 0 and len(tok) > 3:
-                marked = f"^{tok}$"
-                for i in range(len(marked) - 2):
-                    v[self._slot("g:" + marked[i:i + 3], self.dim)] += self.trigram_weight
+            for slot, weight in _token_features(tok, self.dim, self.trigram_weight):
+                acc[slot] = acc.get(slot, 0.0) + weight
+        v = np.zeros(self.dim, dtype=np.float64)
+        if acc:
+            v[list(acc.keys())] = list(acc.values())
         np.sqrt(v, out=v)  # sub-linear term frequency
         n = np.linalg.norm(v)
         if n > 0:
