@@ -355,7 +355,9 @@ def run_ours(args):
                        if used_path != native.PATH_MMA else "bf16 rows x bf16 queries on tcgen05, fp32 accumulate in TMEM (K3)"),
         "roofline": roof,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": B * k * 8,
-                "api": "ShardedIndex.query -> cv_query_device (C-ABI) with pinned host buffers"},
+                "api": ("ShardedIndex.query -> cv_query (C-ABI, host buffers in and out; the query rides in the kernel "
+                        "parameters, the keys land in page-locked host memory)" if world == 1 else
+                        "ShardedIndex.query -> cv_query_device_exchange (C-ABI) with pinned host buffers")},
         "gpu_launches": launches,
         "clocks": clk.summary(),
         "build_seconds": t_build, "rows_per_gpu": local_rows,

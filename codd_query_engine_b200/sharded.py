@@ -142,6 +142,10 @@ class ShardedIndex:
         q = np.ascontiguousarray(queries, dtype=np.float32)
         if q.ndim == 1:
             q = q[None, :]
+        if self.world == 1 and self.device.type == "cuda":
+            # one shard: the C-ABI's own host entry point (cv_query) -- for interactive batches it has no
+            # copy-engine operations or stream synchronise on the path (see native.NativeIndex.query)
+            return self.local.query(q, k, **kw)
         B = q.shape[0]
         key = (B, k)
         if key not in self._host:
