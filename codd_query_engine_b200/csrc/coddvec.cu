@@ -705,25 +705,31 @@ int64_t cv_peer_exchange_bytes(int32_t world, int32_t max_queries, int32_t max_k
     return (flags + keys) * static_cast<int64_t>(sizeof(uint64_t));
 }
 
-int cv_query_device_exchange(cv_index* idx, const float* d_q, const cv_query_params* p, const cv_peer_exchange* px,
-                             uint64_t seq, uint64_t* d_out_keys, void* stream) {
-    int rc = check_query_params(idx, d_q, p);
-    if (rc) return rc;
-    if (!d_out_keys || !px) return fail(CV_ERR_INVALID, "null argument");
+// validate a cv_peer_exchange against the batch and turn it into the kernels' PeerExchange
+static int resolve_exchange(const cv_query_params* p, const cv_peer_exchange* px, uint64_t seq, PeerExchange* dx) {
     if (px->world < 2 || px->world > CV_MAX_PEERS || px->rank < 0 || px->rank >= px->world)
         return fail(CV_ERR_INVALID, "bad peer exchange: world=%d rank=%d", px->world, px->rank);
     if (p->n_queries > px->max_queries || p->k > px->max_k)
         return fail(CV_ERR_INVALID, "batch %d x k %d exceeds the exchange buffer capacity %d x %d", p->n_queries, p->k,
                     px->max_queries, px->max_k);
     if (seq == 0) return fail(CV_ERR_INVALID, "seq must start at 1");
-    PeerExchange dx;
-    dx.world = px->world;
-    dx.rank = px->rank;
-    dx.max_q = px->max_queries;
-    dx.max_k = px->max_k;
-    for (int g = 0; g < kMaxPeers; ++g) dx.base[g] = g < px->world ? reinterpret_cast<uint64_t*>(px->buffers[g]) : nullptr;
+    dx->world = px->world;
+    dx->rank = px->rank;
+    dx->max_q = px->max_queries;
+    dx->max_k = px->max_k;
+    for (int g = 0; g < kMaxPeers; ++g) dx->base[g] = g < px->world ? reinterpret_cast<uint64_t*>(px->buffers[g]) : nullptr;
     for (int g = 0; g < px->world; ++g)
-        if (!dx.base[g]) return fail(CV_ERR_INVALID, "peer buffer %d is null", g);
+        if (!dx->base[g]) return fail(CV_ERR_INVALID, "peer buffer %d is null", g);
+    return CV_OK;
+}
+
+int cv_query_device_exchange(cv_index* idx, const float* d_q, const cv_query_params* p, const cv_peer_exchange* px,
+                             uint64_t seq, uint64_t* d_out_keys, void* stream) {
+    int rc = check_query_params(idx, d_q, p);
+    if (rc) return rc;
+    if (!d_out_keys || !px) return fail(CV_ERR_INVALID, "null argument");
+    PeerExchange dx;
+    if ((rc = resolve_exchange(p, px, seq, &dx))) return rc;
     DeviceGuard dg(idx->cfg.device);
     if (!dg.ok) return fail(CV_ERR_CUDA, "cudaSetDevice(%d) failed", idx->cfg.device);
     std::shared_lock<std::shared_mutex> rd(idx->overwrite_mu);
@@ -740,10 +746,9 @@ int cv_query_device_exchange(cv_index* idx, const float* d_q, const cv_query_par
     return rc;
 }
 
-int cv_query(cv_index* idx, const float* q, const cv_query_params* p, float* out_scores, int64_t* out_rows,
-             int32_t* out_counts) {
-    int rc = check_query_params(idx, q, p);
-    if (rc) return rc;
+static int query_host(cv_index* idx, const float* q, const cv_query_params* p, const PeerExchange* px, uint64_t seq,
+                      float* out_scores, int64_t* out_rows, int32_t* out_counts) {
+    int rc = CV_OK;
     const int B = p->n_queries, k = p->k;
     const size_t qn = static_cast<size_t>(B) * idx->D;
     for (size_t i = 0; i < qn; ++i) {
@@ -791,7 +796,7 @@ int cv_query(cv_index* idx, const float* q, const cv_query_params* p, float* out
             d_mask = c->d_mask.p;
         }
     }
-    rc = enqueue_query(idx, c, s, q_arg, p, d_mask, out_arg, nullptr, 0, nullptr, 0, direct ? &df : nullptr);
+    rc = enqueue_query(idx, c, s, q_arg, p, d_mask, out_arg, nullptr, 0, px, seq, direct ? &df : nullptr);
     if (rc) { (void)cudaStreamSynchronize(s); return rc; }
     if (!direct) CV_CUDA(cudaMemcpyAsync(c->h_out.p, c->d_out.p, sizeof(uint64_t) * B * k, cudaMemcpyDeviceToHost, s));
     CV_CUDA(cudaEventRecord(c->busy, s));
@@ -809,6 +814,23 @@ int cv_query(cv_index* idx, const float* q, const cv_query_params* p, float* out
         }
     }
     return CV_OK;
+}
+
+int cv_query(cv_index* idx, const float* q, const cv_query_params* p, float* out_scores, int64_t* out_rows,
+             int32_t* out_counts) {
+    int rc = check_query_params(idx, q, p);
+    if (rc) return rc;
+    return query_host(idx, q, p, nullptr, 0, out_scores, out_rows, out_counts);
+}
+
+int cv_query_exchange(cv_index* idx, const float* q, const cv_query_params* p, const cv_peer_exchange* px, uint64_t seq,
+                      float* out_scores, int64_t* out_rows, int32_t* out_counts) {
+    int rc = check_query_params(idx, q, p);
+    if (rc) return rc;
+    if (!px) return fail(CV_ERR_INVALID, "null argument");
+    PeerExchange dx;
+    if ((rc = resolve_exchange(p, px, seq, &dx))) return rc;
+    return query_host(idx, q, p, &dx, seq, out_scores, out_rows, out_counts);
 }
 
 }  // extern "C"

@@ -127,6 +127,8 @@ def load_library() -> ctypes.CDLL:
         "cv_peer_exchange_bytes": (i64, [i32, i32, i32]),
         "cv_query_device_exchange": (ctypes.c_int, [vp, vp, ctypes.POINTER(_QueryParams), ctypes.POINTER(_PeerExchange),
                                                     u64, vp, vp]),
+        "cv_query_exchange": (ctypes.c_int, [vp, vp, ctypes.POINTER(_QueryParams), ctypes.POINTER(_PeerExchange),
+                                             u64, vp, vp, vp]),
         "cv_merge_keys_device": (ctypes.c_int, [i32, vp, i32, i32, i32, i32, vp, vp]),
         "cv_decode_keys": (None, [vp, i64, vp, vp]),
         "cv_encode_key": (u64, [ctypes.c_float, u32]),
@@ -151,7 +153,7 @@ def load_library() -> ctypes.CDLL:
 
 EXPORTED_SYMBOLS = (
     "cv_create", "cv_destroy", "cv_upsert", "cv_upsert_device", "cv_query", "cv_query_device",
-    "cv_peer_exchange_bytes", "cv_query_device_exchange", "cv_merge_keys_device", "cv_decode_keys",
+    "cv_peer_exchange_bytes", "cv_query_device_exchange", "cv_query_exchange", "cv_merge_keys_device", "cv_decode_keys",
     "cv_encode_key", "cv_get_rows", "cv_load_rows", "cv_debug_mma_scores", "cv_count", "cv_dim",
     "cv_set_profiling", "cv_stats", "cv_synchronize", "cv_last_error", "cv_version",
 )
@@ -329,6 +331,24 @@ class NativeIndex:
         p = _QueryParams(int(B), int(k), int(ns_code), int(label_code), None, int(path), 0)
         _check(self._lib.cv_query_device_exchange(self._h, q_ptr, ctypes.byref(p), ctypes.byref(px), int(seq),
                                                   out_keys_ptr, _stream_arg(stream)))
+
+    def query_exchange(self, queries: np.ndarray, k: int, px: _PeerExchange, seq: int, ns_code: int = ANY,
+                       label_code: int = ANY, path: int = PATH_AUTO):
+        """Host API of the row-sharded search (every rank calls it with the same queries and seq).  Returns the
+        GLOBAL (scores [B][k], rows [B][k] (-1 pad), counts [B]) on every rank."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise ValueError(f"queries must be [B][{self.dim}], got {q.shape}")
+        B = q.shape[0]
+        p = _QueryParams(B, int(k), int(ns_code), int(label_code), None, int(path), 0)
+        scores = np.empty((B, int(k)), dtype=np.float32)
+        rows = np.empty((B, int(k)), dtype=np.int64)
+        counts = np.empty(B, dtype=np.int32)
+        _check(self._lib.cv_query_exchange(self._h, _ptr(q), ctypes.byref(p), ctypes.byref(px), int(seq), _ptr(scores),
+                                           _ptr(rows), _ptr(counts)))
+        return scores, rows, counts
 
     # -- readback / bookkeeping
     def get_rows(self, rows, want_vectors: bool = True):

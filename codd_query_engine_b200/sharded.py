@@ -14,6 +14,7 @@ torch is used for what it is good at here: device buffers, streams and torch.dis
 
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import numpy as np
@@ -147,6 +148,11 @@ class ShardedIndex:
             # copy-engine operations or stream synchronise on the path (see native.NativeIndex.query)
             return self.local.query(q, k, **kw)
         B = q.shape[0]
+        if (self.world > 1 and self._px is not None and B <= self._px_caps[0] and k <= self._px_caps[1]
+                and os.environ.get("CODDVEC_HOST_EXCHANGE", "1") != "0"):
+            # fused exchange through the C-ABI's host entry point: no torch copies or stream synchronise around it
+            self._seq += 1
+            return self.local.query_exchange(q, k, self._px, self._seq, **kw)
         key = (B, k)
         if key not in self._host:
             pin = self.device.type == "cuda"

@@ -137,6 +137,12 @@ typedef struct cv_peer_exchange {
 int64_t cv_peer_exchange_bytes(int32_t world, int32_t max_queries, int32_t max_k);
 int cv_query_device_exchange(cv_index* idx, const float* d_q, const cv_query_params* p, const cv_peer_exchange* px,
                              uint64_t seq, uint64_t* d_out_keys, void* stream);
+/* The same search with HOST buffers, synchronous like cv_query (every rank passes the same queries): replaces
+ * Collection.query (metrics_semantic_metadata_store.py:314-316) when the collection is row-sharded over GPUs.
+ * Interactive batches take cv_query's low-latency path (queries in the kernel parameters, keys written to
+ * page-locked host memory, completion by a polled flag). */
+int cv_query_exchange(cv_index* idx, const float* q, const cv_query_params* p, const cv_peer_exchange* px,
+                      uint64_t seq, float* out_scores, int64_t* out_rows, int32_t* out_counts);
 
 /* K4: merge G per-shard key lists [G][B][k_in] (device) into [B][k_out] (device) on `stream`
  * of `device`.  Used after the NCCL all-gather of per-GPU top-k. */
