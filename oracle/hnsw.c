@@ -329,6 +329,243 @@ int hnsw_add(hnsw_t* h, const float* x, int64_t n) {
     return 0;
 }
 
+/* ---- concurrent insertion (what `add_items(..., num_threads)` of the library the reference uses does for a
+ * batch).  Test-infrastructure convenience: it makes the recall / timing report practical at 1M rows.  One
+ * lock per element guards its link lists; a thread never holds two locks (read a list: lock, copy, unlock;
+ * add a back-link: lock the neighbour, modify, unlock), so there is no lock-order to get wrong.  Vectors and
+ * levels of the whole batch are stored before the threads start; an element becomes reachable when its first
+ * back-link lands.  The resulting graph depends on the interleaving (as the library's does). ---- */
+#ifdef _OPENMP
+typedef struct {
+    omp_lock_t* node;
+    omp_lock_t global; /* entry point + top level */
+} par_locks_t;
+
+static int read_links(const hnsw_t* h, par_locks_t* L, int id, int lev, int* buf) {
+    omp_set_lock(&L->node[id]);
+    const int* l = links_of(h, id, lev);
+    const int cnt = l[0];
+    memcpy(buf, l + 1, sizeof(int) * (size_t)cnt);
+    omp_unset_lock(&L->node[id]);
+    return cnt;
+}
+
+static int64_t search_layer_par(const hnsw_t* h, par_locks_t* L, const float* q, int ep, float ep_dist, int ef, int lev,
+                                uint32_t* visited, uint32_t tag, heap_t* top, heap_t* cand, int* nbuf) {
+    int64_t evals = 0;
+    top->n = 0;
+    cand->n = 0;
+    pair_t e = {ep_dist, ep};
+    heap_push(top, e);
+    heap_push(cand, e);
+    visited[ep] = tag;
+    float bound = ep_dist;
+    while (cand->n > 0) {
+        pair_t c = cand->a[0];
+        if (c.d > bound && top->n >= ef) break;
+        heap_pop(cand);
+        const int cnt = read_links(h, L, c.id, lev, nbuf);
+        for (int j = 0; j < cnt; ++j) {
+            const int nb = nbuf[j];
+            if (visited[nb] == tag) continue;
+            visited[nb] = tag;
+            const float d = dist_ip(q, h->data + (size_t)nb * (size_t)h->dim, h->dim);
+            ++evals;
+            if (top->n < ef || d < bound) {
+                pair_t p = {d, nb};
+                heap_push(cand, p);
+                heap_push(top, p);
+                if (top->n > ef) heap_pop(top);
+                bound = top->a[0].d;
+            }
+        }
+    }
+    return evals;
+}
+
+/* select_heuristic without the shared counter (threads keep their own) */
+static int select_heuristic_par(const hnsw_t* h, pair_t* cands, int nc, int M, int* out, int64_t* evals) {
+    if (nc <= M) {
+        for (int i = 0; i < nc; ++i) out[i] = cands[i].id;
+        return nc;
+    }
+    qsort(cands, (size_t)nc, sizeof(pair_t), cmp_pair_asc);
+    int kept = 0;
+    for (int i = 0; i < nc && kept < M; ++i) {
+        const float* ci = h->data + (size_t)cands[i].id * (size_t)h->dim;
+        int good = 1;
+        for (int j = 0; j < kept; ++j) {
+            const float d = dist_ip(ci, h->data + (size_t)out[j] * (size_t)h->dim, h->dim);
+            ++*evals;
+            if (d < cands[i].d) { good = 0; break; }
+        }
+        if (good) out[kept++] = cands[i].id;
+    }
+    return kept;
+}
+
+static void insert_par(hnsw_t* h, par_locks_t* L, int id, uint32_t* visited, uint32_t* tag, heap_t* top, heap_t* cand,
+                       pair_t* scratch, int* sel, int* nbuf, int64_t* evals) {
+    const float* v = h->data + (size_t)id * (size_t)h->dim;
+    const int lev = h->level[id];
+    omp_set_lock(&L->global);
+    int ep = h->enter;
+    const int maxl = h->maxlevel;
+    omp_unset_lock(&L->global);
+    float epd = dist_ip(v, h->data + (size_t)ep * (size_t)h->dim, h->dim);
+    ++*evals;
+    for (int l = maxl; l > lev; --l) {
+        int changed = 1;
+        while (changed) {
+            changed = 0;
+            const int cnt = read_links(h, L, ep, l, nbuf);
+            for (int j = 0; j < cnt; ++j) {
+                const float d = dist_ip(v, h->data + (size_t)nbuf[j] * (size_t)h->dim, h->dim);
+                ++*evals;
+                if (d < epd) { epd = d; ep = nbuf[j]; changed = 1; }
+            }
+        }
+    }
+    for (int l = lev < maxl ? lev : maxl; l >= 0; --l) {
+        ++*tag;
+        *evals += search_layer_par(h, L, v, ep, epd, h->efc, l, visited, *tag, top, cand, nbuf);
+        int nc = 0;
+        for (int i = 0; i < top->n; ++i)
+            if (top->a[i].id != id) scratch[nc++] = top->a[i]; /* (a concurrent back-link can make me reachable) */
+        if (nc == 0) continue;
+        int best = 0;
+        for (int i = 1; i < nc; ++i)
+            if (scratch[i].d < scratch[best].d) best = i;
+        ep = scratch[best].id;
+        epd = scratch[best].d;
+        const int ns = select_heuristic_par(h, scratch, nc, h->M, sel, evals);
+        const int maxm = l == 0 ? h->maxM0 : h->M;
+        omp_set_lock(&L->node[id]);
+        {   /* merge with back-links other threads may already have given me */
+            int* mine = links_of(h, id, l);
+            int have = mine[0];
+            for (int i = 0; i < ns && have < maxm; ++i) {
+                int dup = 0;
+                for (int j = 1; j <= have; ++j)
+                    if (mine[j] == sel[i]) { dup = 1; break; }
+                if (!dup) mine[++have] = sel[i];
+            }
+            mine[0] = have;
+        }
+        omp_unset_lock(&L->node[id]);
+        for (int i = 0; i < ns; ++i) {
+            const int nb = sel[i];
+            omp_set_lock(&L->node[nb]);
+            int* ls = links_of(h, nb, l);
+            int dup = 0;
+            for (int j = 1; j <= ls[0]; ++j)
+                if (ls[j] == id) { dup = 1; break; }
+            if (!dup) {
+                if (ls[0] < maxm) {
+                    ls[1 + ls[0]] = id;
+                    ++ls[0];
+                } else {
+                    const float* nbv = h->data + (size_t)nb * (size_t)h->dim;
+                    pair_t* c2 = scratch;
+                    int n2 = 0;
+                    c2[n2].d = dist_ip(nbv, v, h->dim);
+                    c2[n2++].id = id;
+                    for (int j = 1; j <= ls[0]; ++j) {
+                        c2[n2].d = dist_ip(nbv, h->data + (size_t)ls[j] * (size_t)h->dim, h->dim);
+                        c2[n2++].id = ls[j];
+                    }
+                    *evals += n2;
+                    int keep[128];
+                    const int nk = select_heuristic_par(h, c2, n2, maxm, keep, evals);
+                    ls[0] = nk;
+                    for (int j = 0; j < nk; ++j) ls[1 + j] = keep[j];
+                }
+            }
+            omp_unset_lock(&L->node[nb]);
+        }
+    }
+    if (lev > maxl) {
+        omp_set_lock(&L->global);
+        if (lev > h->maxlevel) {
+            h->maxlevel = lev;
+            h->enter = id;
+        }
+        omp_unset_lock(&L->global);
+    }
+}
+#endif
+
+/* Insert n fp32 rows with `threads` OpenMP threads (<= 1 or no OpenMP: the sequential hnsw_add).  0 = ok. */
+int hnsw_add_parallel(hnsw_t* h, const float* x, int64_t n, int threads) {
+#ifndef _OPENMP
+    (void)threads;
+    return hnsw_add(h, x, n);
+#else
+    if (threads <= 1 || n < 2) return hnsw_add(h, x, n);
+    if (h->n + n > h->cap || h->M > 63) return -1;
+    int64_t first = 0;
+    if (h->n == 0) { /* the graph needs an entry point before anyone can search it */
+        if (hnsw_add(h, x, 1) != 0) return -1;
+        first = 1;
+    }
+    const int64_t base = h->n;
+    for (int64_t i = first; i < n; ++i) { /* store vectors, draw levels, allocate link lists -- sequentially */
+        const int id = (int)(base + (i - first));
+        const float* xi = x + (size_t)i * (size_t)h->dim;
+        float* v = h->data + (size_t)id * (size_t)h->dim;
+        if (h->cosine) {
+            double ss = 0.0;
+            for (int d = 0; d < h->dim; ++d) ss += (double)xi[d] * (double)xi[d];
+            const float nrm = (float)sqrt(ss);
+            const float inv = nrm > 0.0f ? 1.0f / nrm : 1.0f;
+            for (int d = 0; d < h->dim; ++d) v[d] = xi[d] * inv;
+        } else {
+            memcpy(v, xi, sizeof(float) * (size_t)h->dim);
+        }
+        double u = ((double)(splitmix64(&h->rng) >> 11) + 1.0) * (1.0 / 9007199254740993.0);
+        const int lev = (int)(-log(u) * h->mult);
+        h->level[id] = lev;
+        h->linkup[id] = lev > 0 ? (int*)calloc((size_t)lev * (size_t)(1 + h->M), sizeof(int)) : NULL;
+        h->link0[(size_t)id * (size_t)(1 + h->maxM0)] = 0;
+    }
+    const int64_t total = base + (n - first);
+    par_locks_t L;
+    L.node = (omp_lock_t*)malloc(sizeof(omp_lock_t) * (size_t)total);
+    for (int64_t i = 0; i < total; ++i) omp_init_lock(&L.node[i]);
+    omp_init_lock(&L.global);
+    h->n = total; /* every id below `total` has a vector, a level and (empty) link lists */
+    int64_t evals_total = 0;
+#pragma omp parallel num_threads(threads) reduction(+ : evals_total)
+    {
+        uint32_t* visited = (uint32_t*)calloc((size_t)total, sizeof(uint32_t));
+        heap_t top, cand;
+        heap_init(&top, h->efc + 2, +1);
+        heap_init(&cand, 4 * h->efc, -1);
+        const int sc = (h->efc > h->maxM0 ? h->efc : h->maxM0) + 2;
+        pair_t* scratch = (pair_t*)malloc(sizeof(pair_t) * (size_t)sc);
+        int* sel = (int*)malloc(sizeof(int) * (size_t)(h->maxM0 + 1));
+        int* nbuf = (int*)malloc(sizeof(int) * (size_t)(h->maxM0 + 1));
+        uint32_t tag = 0;
+        int64_t evals = 0;
+#pragma omp for schedule(dynamic, 8)
+        for (int64_t id = base; id < total; ++id)
+            insert_par(h, &L, (int)id, visited, &tag, &top, &cand, scratch, sel, nbuf, &evals);
+        evals_total += evals;
+        free(nbuf);
+        free(sel);
+        free(scratch);
+        heap_free(&cand);
+        heap_free(&top);
+        free(visited);
+    }
+    h->dist_evals += evals_total;
+    for (int64_t i = 0; i < total; ++i) omp_destroy_lock(&L.node[i]);
+    omp_destroy_lock(&L.global);
+    free(L.node);
+    return 0;
+#endif
+}
+
 /* Alg. 5 K-NN-SEARCH for nq queries.  out_ids [nq][k] (-1 padded), out_dist [nq][k] ascending
  * (1 - cosine).  threads <= 1: one query after another (how the reference issues them,
  * store.py:314-316 is one query per call); > 1: OpenMP over queries. */

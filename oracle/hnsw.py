@@ -45,6 +45,8 @@ def _lib():
         lib.hnsw_dist_evals.restype = ctypes.c_int64
         lib.hnsw_add.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
         lib.hnsw_add.restype = ctypes.c_int
+        lib.hnsw_add_parallel.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]
+        lib.hnsw_add_parallel.restype = ctypes.c_int
         lib.hnsw_search.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
                                     ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         lib.hnsw_search.restype = ctypes.c_int
@@ -62,11 +64,15 @@ class HnswIndex:
         if not self._h:
             raise MemoryError("hnsw_create failed")
 
-    def add(self, x: np.ndarray) -> None:
+    def add(self, x: np.ndarray, threads: int = 1) -> None:
+        """threads <= 1: one insertion after another (deterministic); > 1: concurrent insertion of the batch, as
+        the library's add_items(num_threads) does (graph depends on the interleaving)."""
         x = np.ascontiguousarray(x, dtype=np.float32)
         if x.ndim != 2 or x.shape[1] != self.dim:
             raise ValueError("embeddings must be [n][dim]")
-        if _lib().hnsw_add(self._h, x.ctypes.data, x.shape[0]) != 0:
+        rc = (_lib().hnsw_add(self._h, x.ctypes.data, x.shape[0]) if threads <= 1 else
+              _lib().hnsw_add_parallel(self._h, x.ctypes.data, x.shape[0], int(threads)))
+        if rc != 0:
             raise RuntimeError("hnsw_add: capacity exceeded")
 
     def search(self, q: np.ndarray, k: int, ef_search: int = REF_EF_SEARCH, threads: int = 1):

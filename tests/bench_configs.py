@@ -4,6 +4,7 @@ it uses the oracle as its checker) (bench.py covers configs[1] and the 100M corp
 
   cfg1  the reference's CPU-runnable case: 10k x 384 in the semantic store, 1 query, top-10 -- end to end through
         Collection.query / search_metadata, beside the exact CPU oracle and the HNSW restatement (timing + recall@k)
+  cfg2r (on request) 1M x 384 clustered rows: this package's exact search beside the HNSW restatement (recall + timing)
   cfg3  10M x 768 bf16, fused namespace predicate at 10 % selectivity, top-50, batch 1 (K2 PRED)
   cfg5  bulk upsert of 1M x 384 fp32 host embeddings in chunks of 1000 (MAX_BULK_OPERATIONS,
         codd_dal/metrics/metrics_semantic_metadata_store.py:23) interleaved with live top-10 queries
@@ -246,8 +247,53 @@ def cfg1(rows=10_000):
             "parity_vs_oracle": bool(parity), "store_result_shape_ok": bool(shape_ok)}
 
 
+def cfg2r(rows):
+    """BASELINE configs[1]'s corpus size with structure (256 Gaussian centroids, sigma 0.3): this package's exact
+    one-query-per-call search beside the reference's index type -- the HNSW restatement with the reference's
+    parameters, graph built with all host threads (add_items(num_threads) analogue), queried on one thread --
+    and the recall@10 of both against the exact CPU oracle.  (Only on request: the graph build takes ~a minute.)"""
+    from oracle import hnsw  # checker / baseline only
+
+    D, k, nq = 384, 10, 200
+    rng = np.random.default_rng(0)
+    cent = rng.standard_normal((256, D), dtype=np.float32)
+    x = cent[rng.integers(0, 256, rows)] + 0.3 * rng.standard_normal((rows, D), dtype=np.float32)
+    qs = cent[rng.integers(0, 256, nq)] + 0.3 * rng.standard_normal((nq, D), dtype=np.float32)
+    idx = native.NativeIndex(D, capacity_rows=rows, max_rows=rows)
+    idx.upsert(x)
+    for i in range(20):
+        idx.query(qs[i:i + 1], k)
+    t0 = time.perf_counter()
+    ours = np.concatenate([idx.query(qs[i:i + 1], k)[1] for i in range(nq)])
+    t_ours = (time.perf_counter() - t0) / nq
+    stored, scale, _, _ = idx.get_rows(np.arange(rows))
+    idx.close()
+    lib = bench.load_c_oracle()
+    t_bf, threads, _ = bench.cpu_time_queries(lib, stored, scale, qs[:1], k, 20)
+    _, exact = bf.unpack_keys(bench.cpu_time_queries(lib, stored, scale, qs, k, 1)[2])
+    t0 = time.perf_counter()
+    graph = hnsw.HnswIndex(D, rows)
+    graph.add(x, threads=os.cpu_count() or 1)
+    t_graph = time.perf_counter() - t0
+    graph.search(qs[:20], k)
+    t0 = time.perf_counter()
+    approx = np.concatenate([graph.search(qs[i:i + 1], k)[0] for i in range(nq)])
+    t_hnsw = (time.perf_counter() - t0) / nq
+    graph.close()
+    return {"config": "cfg2r", "workload": f"{rows} x 384 clustered rows, 1 query per call, top-{k}",
+            "ours_e2e_ms_per_query": t_ours * 1e3, "ours_e2e_qps": 1 / t_ours,
+            "recall_at_k_ours_vs_exact": hnsw.recall_at_k(ours, exact),
+            "hnsw_port_ms_per_query_1_thread": t_hnsw * 1e3, "hnsw_port_qps_1_thread": 1 / t_hnsw,
+            "hnsw_port_build_s": t_graph, "hnsw_port_build_threads": os.cpu_count() or 1,
+            "recall_at_k_hnsw_vs_exact": hnsw.recall_at_k(approx, exact),
+            "cpu_exact_oracle_ms_per_query": float(np.median(t_bf)) * 1e3, "cpu_exact_oracle_threads": threads,
+            "hnsw_params": "cosine M=16 ef_construction=200 ef_search=100"}
+
+
 def main():
     want = [a for a in sys.argv[1:] if a.startswith("cfg")] or ["cfg1", "cfg3", "cfg5"]
+    if "cfg2r" in want:
+        print(json.dumps(cfg2r(arg("--rows2", 1_000_000))), flush=True)
     if "cfg1" in want:
         print(json.dumps(cfg1()), flush=True)
     if "cfg3" in want:

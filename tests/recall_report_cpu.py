@@ -2,9 +2,10 @@
 """CPU-only recall / timing report of the HNSW restatement (oracle/hnsw.c, the reference's collection parameters)
 against the exact brute-force oracle -- which IS this package's answer (GPU parity tests) -- at sizes beyond cfg1.
 
-    python tests/recall_report_cpu.py [--rows N] [--kind clustered|gaussian] [--queries Q]
+    python tests/recall_report_cpu.py [--rows N] [--kind clustered|gaussian] [--queries Q] [--threads T]
 
-One JSON line per run.  Single-threaded graph build (like one upsert after another) takes minutes at 1M rows."""
+One JSON line per run.  A single-threaded graph build (one upsert after another) takes minutes at 1M rows;
+--threads T inserts concurrently, as the library's add_items(num_threads) does."""
 import json
 import os
 import sys
@@ -38,9 +39,10 @@ def main():
     stored, scale = bf.normalise_store(x)
     t_bf, threads, keys = bench.cpu_time_queries(lib, stored, scale, q[:1], k, 5)
     _, exact = bf.unpack_keys(bench.cpu_time_queries(lib, stored, scale, q, k, 1)[2])
+    threads = arg("--threads", 1)
     t0 = time.perf_counter()
     g = hnsw.HnswIndex(D, n)
-    g.add(x)
+    g.add(x, threads=threads)
     t_build = time.perf_counter() - t0
     g.search(q[:10], k)
     g.dist_evals(reset=True)
@@ -50,7 +52,7 @@ def main():
     evals = g.dist_evals() / nq
     print(json.dumps({"rows": n, "dim": D, "kind": kind, "k": k, "queries": nq,
                       "hnsw_params": "cosine, M=16, ef_construction=200, ef_search=100",
-                      "hnsw_build_s_1_thread": t_build, "hnsw_query_ms_1_thread": t_q * 1e3, "hnsw_dist_evals_per_query": evals,
+                      "hnsw_build_s": t_build, "hnsw_build_threads": threads, "hnsw_query_ms_1_thread": t_q * 1e3, "hnsw_dist_evals_per_query": evals,
                       "hnsw_max_level": g.max_level, "recall_at_k_hnsw_vs_exact": hnsw.recall_at_k(approx, exact),
                       "exact_cpu_oracle_ms_per_query": float(np.median(t_bf)) * 1e3, "exact_cpu_oracle_threads": threads}), flush=True)
     g.close()

@@ -99,3 +99,30 @@ def test_threads_do_not_change_answers():
     b = g.search(q, 10, threads=4)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
     assert g.dist_evals(reset=True) > 0 and g.dist_evals() == 0
+
+
+def test_concurrent_insertion_builds_an_equally_good_graph():
+    """hnsw_add_parallel (the library's add_items(num_threads) analogue): same recall as the sequential build, every
+    element inserted exactly once, incremental use after a sequential prefix."""
+    rng = np.random.default_rng(8)
+    D, n = 48, 12000
+    cent = rng.standard_normal((32, D)).astype(np.float32)
+    x = (cent[rng.integers(0, 32, n)] + 0.3 * rng.standard_normal((n, D))).astype(np.float32)
+    q = (cent[rng.integers(0, 32, 60)] + 0.3 * rng.standard_normal((60, D))).astype(np.float32)
+    er, _ = exact_rows(x, q, 10)
+    seq = hnsw.HnswIndex(D, n)
+    seq.add(x)
+    par = hnsw.HnswIndex(D, n)
+    par.add(x[:500])
+    par.add(x[500:], threads=4)
+    assert len(par) == len(seq) == n
+    r_seq = hnsw.recall_at_k(seq.search(q, 10)[0], er)
+    ids, dist = par.search(q, 10)
+    r_par = hnsw.recall_at_k(ids, er)
+    assert r_par >= r_seq - 0.02 and r_par >= 0.95
+    assert (ids >= 0).all() and (np.diff(dist, axis=1) >= 0).all()
+    assert all(len(set(r)) == len(r) for r in ids.tolist())
+    # every element is findable as its own nearest neighbour (nothing was lost or left unlinked)
+    probe = rng.integers(0, n, 200)
+    own, _ = par.search(x[probe], 1, ef_search=200)
+    assert (own[:, 0] == probe).mean() >= 0.99
