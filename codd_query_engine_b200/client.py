@@ -96,6 +96,7 @@ class Collection:
         self._free_rows: list[int] = []
         self._ns_codes: dict[Any, int] = {}
         self._label_codes: dict[Any, int] = {}
+        self._ns_rows: dict[int, int] = {}  # live rows per namespace code (selectivity estimate for filtered batches)
 
     # ------------------------------------------------------------------ helpers
     def _ensure_index(self, dim: int) -> NativeIndex:
@@ -116,6 +117,30 @@ class Collection:
             code = len(table) + 1
             table[value] = code
         return code
+
+    def _ns_count(self, metadata, delta: int) -> None:
+        code = self._ns_codes.get((metadata or {}).get("namespace"), 0)
+        self._ns_rows[code] = self._ns_rows.get(code, 0) + delta
+
+    def _filtered_batch_path(self, B: int, compiled) -> int:
+        """Path for a FILTERED batch.  The tensor path scores every row and masks afterwards, the scan path (K2)
+        tests eligibility first and reads only the selected rows -- but needs one pass per 2-4 queries.  With the
+        share of eligible rows known on the host (rows per namespace code, or the bitmask's population count),
+        small batches over selective filters go to the scan: cost model in units of one full-corpus pass, K3 = 1,
+        K2 = B * (selectivity + code-column share) * (1 for rows up to 384-d, 2 above: one query per full-speed
+        pass), taken only when it wins by a clear margin.  Exact either way."""
+        if B < 2 or self._index is None:
+            return native.PATH_AUTO
+        live = max(len(self._row_of), 1)
+        if compiled.mask_words is not None:
+            eligible = int(np.unpackbits(compiled.mask_words.view(np.uint8)).sum())
+        elif compiled.ns_code != native.ANY:
+            eligible = self._ns_rows.get(compiled.ns_code, 0)
+        else:
+            return native.PATH_AUTO  # a label-only filter: no count at hand
+        selectivity = min(eligible / live, 1.0)
+        per_query = (selectivity + 0.05) * (1.0 if self._index.dim <= 384 else 2.0)
+        return native.PATH_SCAN if B * per_query < 1.0 else native.PATH_AUTO
 
     def _embed_texts(self, texts: Sequence[str]) -> np.ndarray:
         out = np.asarray(self._embed(list(texts)), dtype=np.float32)
@@ -209,6 +234,9 @@ class Collection:
                 self._alive = np.concatenate([self._alive, np.zeros(grow, dtype=bool)])
             for j, doc_id in enumerate(ids):
                 r = int(got[j])
+                if self._alive[r]:  # replacing a live row: it leaves its old namespace
+                    self._ns_count(self._metadatas[r], -1)
+                self._ns_count(mds[j], +1)
                 self._row_of[doc_id] = r
                 self._ids[r] = doc_id
                 self._metadatas[r] = mds[j]
@@ -259,6 +287,7 @@ class Collection:
                 validate_where(where)
                 targets = [r for r in targets if evaluate(where, self._metadatas[r])]
             for r in targets:
+                self._ns_count(self._metadatas[r], -1)
                 self._row_of.pop(self._ids[r], None)
                 self._ids[r] = None
                 self._metadatas[r] = None
@@ -375,7 +404,7 @@ class Collection:
                 return empty()
             k = min(int(n_results), native.MAX_K, len(self._row_of))
             scores, rows, counts = self._index.query(q, k, ns_code=compiled.ns_code, label_code=compiled.label_code,
-                                                     mask=compiled.mask_words)
+                                                     mask=compiled.mask_words, path=self._filtered_batch_path(B, compiled))
             if self._metric == native.METRIC_COSINE:
                 np.clip(scores, -1.0, 1.0, out=scores)
             res = empty()
@@ -449,6 +478,9 @@ class Collection:
         if len(coll._ids) != n:
             raise ValueError(f"snapshot {directory} is truncated: {len(coll._ids)} records for {n} rows")
         coll._alive = np.array([i is not None for i in coll._ids], dtype=bool)
+        for r, doc_id in enumerate(coll._ids):
+            if doc_id is not None:
+                coll._ns_count(coll._metadatas[r], +1)
         coll._row_of = {i: r for r, i in enumerate(coll._ids) if i is not None}
         coll._free_rows = [int(r) for r in meta["free_rows"]]
         if dim is not None and n:

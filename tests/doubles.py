@@ -63,6 +63,7 @@ class OracleIndex:
         if not 1 <= k <= 128:
             raise ValueError("coddvec: k must be in [1, 128]")
         self.queries += 1
+        self.last_requested_path = path  # (tests of the client's path choice read it)
         return bf.query(self._stored, self._scale, q, k, metric=self.metric, mask_words=mask, ns=self._ns,
                         ns_code=ns_code, label=self._label, label_code=label_code, row_offset=self.row_offset)
 

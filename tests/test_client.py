@@ -266,3 +266,44 @@ def test_default_embedder_is_deterministic_unit_and_nonnegative():
     assert not a[2].any()
     assert a[0] @ e(["cpu utilization"])[0] > a[3] @ e(["cpu utilization"])[0]
     assert e([]).shape == (0, 384)
+
+
+def test_filtered_batches_choose_the_scan_when_the_filter_is_selective(monkeypatch):
+    """Collection.query hands a FILTERED batch to the scan path (K2: eligibility first, only selected rows are read)
+    when batch size x selectivity says it beats one tensor-path pass over every row; answers are the same either
+    way.  The per-namespace row counts behind the estimate follow upserts, replacements, deletes and snapshots."""
+    from codd_query_engine_b200 import client as client_mod
+    from codd_query_engine_b200 import native
+    from tests.doubles import OracleIndex
+
+    monkeypatch.setattr(client_mod, "NativeIndex", OracleIndex)
+    c = client_mod.Client(endpoint=("paths", "t"))
+    coll = c.get_or_create_collection("c", metadata={"hnsw:space": "cosine"})
+    rng = np.random.default_rng(0)
+    n = 2000
+    x = rng.standard_normal((n, 384)).astype(np.float32)
+    ns = ["rare" if i % 50 == 0 else ("mid" if i % 5 == 1 else "big") for i in range(n)]   # 2 % / 20 % / 78 %
+    coll.upsert(ids=[str(i) for i in range(n)], embeddings=x, metadatas=[{"namespace": s, "k": i % 7} for i, s in enumerate(ns)])
+    assert coll._ns_rows[coll._ns_codes["rare"]] == 40 and coll._ns_rows[coll._ns_codes["mid"]] == 400
+
+    def path_of(B, where):
+        coll.query(query_embeddings=x[:B], n_results=3, where=where)
+        return coll._index.last_requested_path
+
+    assert path_of(1, {"namespace": "rare"}) == native.PATH_AUTO          # one query: AUTO already scans
+    assert path_of(8, {"namespace": "rare"}) == native.PATH_SCAN          # 8 x (0.02 + 0.05) < 1
+    assert path_of(3, {"namespace": "mid"}) == native.PATH_SCAN           # 3 x 0.25 < 1
+    assert path_of(8, {"namespace": "mid"}) == native.PATH_AUTO           # 8 x 0.25 > 1: one tensor pass is cheaper
+    assert path_of(2, {"namespace": "big"}) == native.PATH_AUTO
+    assert path_of(64, None) == native.PATH_AUTO                          # unfiltered
+    assert path_of(4, {"k": {"$in": [3]}}) == native.PATH_SCAN            # bitmask filter, ~14 % of the rows: 4 x 0.19 < 1
+    assert path_of(6, {"k": {"$ne": 3}}) == native.PATH_AUTO              # bitmask filter, ~86 %
+    # the counts follow the collection
+    coll.upsert(ids=["0"], embeddings=x[:1], metadatas=[{"namespace": "mid"}])   # row 0 moves rare -> mid
+    coll.delete(ids=["50"])                                                         # another rare row goes
+    assert coll._ns_rows[coll._ns_codes["rare"]] == 38 and coll._ns_rows[coll._ns_codes["mid"]] == 401
+    # and both paths give the same hits (the double is exact on either)
+    a = coll.query(query_embeddings=x[5:9], n_results=4, where={"namespace": "rare"})
+    b = [coll.query(query_embeddings=x[5 + i], n_results=4, where={"namespace": "rare"})["ids"][0] for i in range(4)]
+    assert a["ids"] == b
+    c.reset()
