@@ -262,6 +262,7 @@ int plan_scan(cv_index* idx, QueryCtx* c, int qb, int k, bool pred, ScanLaunch* 
     if (!fn) return fail(CV_ERR_UNSUPPORTED, "scan path: no kernel for dim=%d with %d queries per pass", idx->D, qb);
     size_t smem = (static_cast<size_t>(kSelCap) + static_cast<size_t>(kScanWarps) * qb * scan_list_cap(k)) * sizeof(uint64_t);
     if (scan_is_wide(nch)) smem += static_cast<size_t>(idx->Dp) * sizeof(float);  // the normalised query
+    else if (scan_queries_in_smem(nch, qb)) smem += static_cast<size_t>(qb) * idx->C * 32;  // queries as 2 x float4 per chunk
     CV_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     int occ = 0;
     CV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kScanThreads, smem));

@@ -234,8 +234,16 @@ __device__ __forceinline__ bool row_valid(uint32_t r) { return r != 0xFFFFFFFFu;
 
 constexpr int kRingCap = 256;  // per-warp ring of eligible rows (predicate scan): >= 128 + max slots - 1
 
+// QS ("queries in shared memory"): variants whose queries would need more than 48 registers per lane
+// (NCH * QB > 6) keep the normalised queries in shared memory instead -- two 16-byte arrays per 8-element chunk
+// (elements 0-3 / 4-7) so that the lanes' LDS.128 reads are conflict-free -- and fetch them per (chunk, query)
+// inside the FMA loop (1 LDS.128 per 16 FMAs).  That keeps every variant at two CTAs per SM; the register
+// variants are unchanged.  The summation order is the register variant's, so results are bit-identical.
+__host__ __device__ constexpr bool scan_queries_in_smem(int nch, int qb) { return nch * qb > 6; }
+
 template <int NCH, int QB, bool PRED>
-__global__ void __launch_bounds__(kScanThreads, (NCH * QB <= 6) ? 2 : 1) k_scan_topk(ScanArgs a) {
+__global__ void __launch_bounds__(kScanThreads, 2) k_scan_topk(ScanArgs a) {
+    constexpr bool QS = scan_queries_in_smem(NCH, QB);
     using row_t = typename ScanRow<PRED>::type;
     constexpr row_t kEmptyRow = static_cast<row_t>(-1);
     constexpr int RPH = scan_rph(NCH, QB);
@@ -247,6 +255,9 @@ __global__ void __launch_bounds__(kScanThreads, (NCH * QB <= 6) ? 2 : 1) k_scan_
     uint64_t* selbuf = reinterpret_cast<uint64_t*>(smem_raw);                 // kSelCap keys (32 KB)
     uint64_t* lists = selbuf + kSelCap;                                       // [warps][QB][cap] candidate buffers
     float* sq = reinterpret_cast<float*>(smem_raw);                           // prologue alias: [QB][D]
+    // QS only: normalised queries behind the lists, [QB][C] x (elements 0-3) then [QB][C] x (elements 4-7)
+    float4* sqlo = reinterpret_cast<float4*>(lists + static_cast<size_t>(kScanWarps) * QB * scan_list_cap(a.k));
+    float4* sqhi = sqlo + QB * a.C;
     __shared__ float s_norm[QB];
     __shared__ int s_cnt;
     __shared__ uint64_t s_red[kScanWarps];
@@ -286,16 +297,25 @@ __global__ void __launch_bounds__(kScanThreads, (NCH * QB <= 6) ? 2 : 1) k_scan_
         if (lane == 0) s_norm[warp] = nrm;
     }
     __syncthreads();
-    float qr[QB][NCH][8];
+    float qr[QS ? 1 : QB][QS ? 1 : NCH][8];
+    if constexpr (QS) {
+        for (int i = tid; i < QB * C * 8; i += kScanThreads) {
+            const int b = i / (C * 8), d = i - b * (C * 8);
+            const float v = (d < a.D) ? __fdiv_rn(sq[b * a.D + d], s_norm[b]) : 0.0f;
+            float* dst = reinterpret_cast<float*>(((d & 4) ? sqhi : sqlo) + b * C + (d >> 3));
+            dst[d & 3] = v;
+        }
+    } else {
 #pragma unroll
-    for (int b = 0; b < QB; ++b)
+        for (int b = 0; b < QB; ++b)
 #pragma unroll
-        for (int c = 0; c < NCH; ++c)
+            for (int c = 0; c < NCH; ++c)
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                int d = (hl + 16 * c) * 8 + e;
-                qr[b][c][e] = (d < a.D) ? __fdiv_rn(sq[b * a.D + d], s_norm[b]) : 0.0f;
-            }
+                for (int e = 0; e < 8; ++e) {
+                    int d = (hl + 16 * c) * 8 + e;
+                    qr[b][c][e] = (d < a.D) ? __fdiv_rn(sq[b * a.D + d], s_norm[b]) : 0.0f;
+                }
+    }
     __syncthreads();  // sq aliases selbuf; everyone is done reading it
 
     // which (row slot, query) this lane ends up holding after the butterfly
@@ -352,6 +372,36 @@ __global__ void __launch_bounds__(kScanThreads, (NCH * QB <= 6) ? 2 : 1) k_scan_
         const float sc = (FAST || DENSE || row_valid(my_row)) ? __ldg(a.scale + my_row) : 0.0f;
 
         float acc[V];
+        if constexpr (QS) {
+            float a0[V], a1[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) { a0[v] = 0.0f; a1[v] = 0.0f; }
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                const int ci = min(hl + 16 * c, C - 1);  // (a chunk past the row's end was loaded as zeros)
+#pragma unroll
+                for (int b = 0; b < QB; ++b) {
+                    const float4 ql = sqlo[b * C + ci], qh = sqhi[b * C + ci];
+#pragma unroll
+                    for (int i = 0; i < RPH; ++i) {
+                        const uint4 w = ld[i][c];
+                        float s0 = a0[i * QB + b], s1 = a1[i * QB + b];
+                        s0 = fmaf(bf16lo_f32(w.x), ql.x, s0);
+                        s1 = fmaf(bf16hi_f32(w.x), ql.y, s1);
+                        s0 = fmaf(bf16lo_f32(w.y), ql.z, s0);
+                        s1 = fmaf(bf16hi_f32(w.y), ql.w, s1);
+                        s0 = fmaf(bf16lo_f32(w.z), qh.x, s0);
+                        s1 = fmaf(bf16hi_f32(w.z), qh.y, s1);
+                        s0 = fmaf(bf16lo_f32(w.w), qh.z, s0);
+                        s1 = fmaf(bf16hi_f32(w.w), qh.w, s1);
+                        a0[i * QB + b] = s0;
+                        a1[i * QB + b] = s1;
+                    }
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc[v] = a0[v] + a1[v];
+        } else {
 #pragma unroll
         for (int i = 0; i < RPH; ++i) {
 #pragma unroll
@@ -371,6 +421,7 @@ __global__ void __launch_bounds__(kScanThreads, (NCH * QB <= 6) ? 2 : 1) k_scan_
                 }
                 acc[i * QB + b] = s0 + s1;
             }
+        }
         }
         const float dot = reduce16<V>(acc, hl);
         const float score = dot * sc;
