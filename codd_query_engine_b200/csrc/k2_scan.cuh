@@ -233,6 +233,15 @@ __device__ __forceinline__ bool row_valid(int64_t r) { return r >= 0; }
 __device__ __forceinline__ bool row_valid(uint32_t r) { return r != 0xFFFFFFFFu; }
 
 constexpr int kRingCap = 256;  // per-warp ring of eligible rows (predicate scan): >= 128 + max slots - 1
+constexpr int kCodeStages = 4; // 128-row steps of code columns in flight per warp (cp.async staging)
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // QS ("queries in shared memory"): variants whose queries would need more than 48 registers per lane
 // (NCH * QB > 6) keep the normalised queries in shared memory instead -- two 16-byte arrays per 8-element chunk
@@ -492,19 +501,27 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_topk(ScanArgs a) {
         // mask word of the NEXT step are loaded before this step's rows are processed, so their latency
         // overlaps the row loads.
         __shared__ __align__(16) uint32_t s_ring[kScanWarps][kRingCap];
+        // Code columns are staged through shared memory with cp.async, kCodeStages 128-row steps ahead: the copies
+        // hold no registers while in flight, so the prefetch can be deep enough to hide the L2/HBM latency even
+        // when almost no row is eligible and a step is only a few dozen instructions long (1 % selectivity).
+        __shared__ __align__(16) uint4 s_codes[kScanWarps][kCodeStages][2][32];  // [stage][ns | label][lane]
         uint32_t* ring = s_ring[warp];
         const uint32_t lt_mask = (1u << lane) - 1u;
         const int64_t blocks = (a.n + 127) / 128;
         const int64_t nwords = (a.n + 31) / 32;
         const bool use_ns = a.ns_code != kAny, use_label = a.label_code != kAny;
-        uint4 nsv, lbv;
         uint32_t mkv;
-        auto fetch = [&](int64_t blk) {
+        // issue the copies of step `blk` into stage `st` (nothing for columns not in use / rows past the end), then
+        // close the group -- one group per step, empty or not, so that wait_group counts steps
+        auto stage_codes = [&](int64_t blk, int st) {
             const int64_t r0 = blk * 128 + 4 * lane;  // 16-byte aligned; the arrays are mapped in 16-byte multiples
-            const bool in = blk < blocks && r0 < a.n;
-            nsv = (in && use_ns) ? __ldg(reinterpret_cast<const uint4*>(a.ns + r0)) : make_uint4(a.ns_code, a.ns_code, a.ns_code, a.ns_code);
-            lbv = (in && use_label) ? __ldg(reinterpret_cast<const uint4*>(a.label + r0))
-                                    : make_uint4(a.label_code, a.label_code, a.label_code, a.label_code);
+            if (blk < blocks && r0 < a.n) {
+                if (use_ns) cp_async16(&s_codes[warp][st][0][lane], a.ns + r0);
+                if (use_label) cp_async16(&s_codes[warp][st][1][lane], a.label + r0);
+            }
+            cp_async_commit();
+        };
+        auto fetch_mask = [&](int64_t blk) {
             const int64_t wi = blk * 4 + (lane >> 3);
             mkv = a.mask ? ((blk < blocks && wi < nwords) ? __ldg(a.mask + wi) : 0u) : 0xFFFFFFFFu;
         };
@@ -517,19 +534,31 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_topk(ScanArgs a) {
             else process(false, false, rows, nullptr);
         };
         uint32_t head = 0, tail = 0;  // warp-uniform; head stays a multiple of S
-        fetch(gw);
+#pragma unroll
+        for (int st = 0; st < kCodeStages; ++st) stage_codes(gw + st * nw, st);
+        fetch_mask(gw);
+        int st = 0;
         for (int64_t blk = gw; blk < blocks; blk += nw) {
-            const uint32_t base = static_cast<uint32_t>(blk * 128) + 4u * lane;
-            const uint32_t mbits = mkv >> ((4 * lane) & 31);
+            cp_async_wait<kCodeStages - 1>();  // this step's group has landed (the younger ones may be in flight)
+            __syncwarp();
             const int64_t rem = a.n - (blk * 128 + 4 * lane);  // rows of this lane's quad that exist
             const int left = rem >= 4 ? 4 : (rem > 0 ? static_cast<int>(rem) : 0);
+            const uint4 none_ns = make_uint4(a.ns_code, a.ns_code, a.ns_code, a.ns_code);
+            const uint4 none_lb = make_uint4(a.label_code, a.label_code, a.label_code, a.label_code);
+            const uint4 nsv = (use_ns && left > 0) ? s_codes[warp][st][0][lane] : none_ns;
+            const uint4 lbv = (use_label && left > 0) ? s_codes[warp][st][1][lane] : none_lb;
+            __syncwarp();  // every lane has read the stage before it is refilled
+            stage_codes(blk + static_cast<int64_t>(kCodeStages) * nw, st);
+            st = st + 1 == kCodeStages ? 0 : st + 1;
+            const uint32_t base = static_cast<uint32_t>(blk * 128) + 4u * lane;
+            const uint32_t mbits = mkv >> ((4 * lane) & 31);
             const bool ok0 = left > 0 && nsv.x == a.ns_code && lbv.x == a.label_code && (mbits & 1u);
             const bool ok1 = left > 1 && nsv.y == a.ns_code && lbv.y == a.label_code && (mbits & 2u);
             const bool ok2 = left > 2 && nsv.z == a.ns_code && lbv.z == a.label_code && (mbits & 4u);
             const bool ok3 = left > 3 && nsv.w == a.ns_code && lbv.w == a.label_code && (mbits & 8u);
             const uint32_t w0 = __ballot_sync(kFullMask, ok0), w1 = __ballot_sync(kFullMask, ok1);
             const uint32_t w2 = __ballot_sync(kFullMask, ok2), w3 = __ballot_sync(kFullMask, ok3);
-            fetch(blk + nw);
+            fetch_mask(blk + nw);
             uint32_t t = tail;
             if (ok0) ring[(t + __popc(w0 & lt_mask)) & (kRingCap - 1)] = base;
             t += __popc(w0);
@@ -546,6 +575,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_topk(ScanArgs a) {
             }
             __syncwarp();  // ring slots read above may be overwritten by the next step's appends
         }
+        cp_async_wait<0>();  // nothing may still be landing in shared memory when the tail reuses it
         if (tail != head) consume(head, tail - head);
     }
 
