@@ -100,7 +100,7 @@ struct PinBuf {
 // (Rows up to 384 elements: two queries still fit one K2 pass at HBM speed -- 0.140 ms against K3's 0.151 ms on
 // 1M x 384 -- four do not, the FMA work doubles again and the pass drops to 3.4 TB/s.)
 constexpr int kAutoScanMaxBatch = 1;
-constexpr int kAutoScanMaxBatchShortRows = 2;
+constexpr int kAutoScanMaxBatchShortRows = 2;  // rows up to 768 elements: two queries per HBM-speed K2 pass
 
 // Per-query scratch.  A context is used by one query batch at a time; `busy` orders reuse on a
 // different stream without blocking the host.
@@ -127,6 +127,7 @@ struct QueryCtx {
         if (d_counter) cudaFree(d_counter);
         if (d_heads) cudaFree(d_heads);
         if (mma.p) cudaFree(mma.p);
+        if (mma.state) cudaFree(mma.state);
         if (busy) cudaEventDestroy(busy);
         if (t0) cudaEventDestroy(t0);
         if (t1) cudaEventDestroy(t1);
@@ -139,6 +140,7 @@ struct QueryCtx {
 struct cv_index {
     cv_config cfg{};
     int D = 0, Dp = 0, C = 0;
+    int64_t row_stride = 1;
     int sm_count = 148;
     int64_t max_rows = 0;
     VmmArray E, scale, ns, label;
@@ -260,10 +262,26 @@ int plan_scan(cv_index* idx, QueryCtx* c, int qb, int k, bool pred, ScanLaunch* 
     const int nch = (idx->C + 15) / 16;
     ScanFn fn = pick_scan(nch, qb, pred);
     if (!fn) return fail(CV_ERR_UNSUPPORTED, "scan path: no kernel for dim=%d with %d queries per pass", idx->D, qb);
-    size_t smem = (static_cast<size_t>(kSelCap) + static_cast<size_t>(kScanWarps) * qb * scan_list_cap(k)) * sizeof(uint64_t);
-    if (scan_is_wide(nch)) smem += static_cast<size_t>(idx->Dp) * sizeof(float);  // the normalised query
-    else if (scan_queries_in_smem(nch, qb)) smem += static_cast<size_t>(qb) * idx->C * 32;  // queries as 2 x float4 per chunk
-    CV_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    auto smem_for = [&](int kk) {
+        size_t b = (static_cast<size_t>(kSelCap) + static_cast<size_t>(kScanWarps) * qb * scan_list_cap(kk)) * sizeof(uint64_t);
+        if (scan_is_wide(nch)) b += static_cast<size_t>(idx->Dp) * sizeof(float);  // the normalised query
+        else if (scan_queries_in_smem(nch, qb)) b += static_cast<size_t>(qb) * idx->C * 32;  // queries as 2 x float4 per chunk
+        return b;
+    };
+    const size_t smem = smem_for(k);
+    // The dynamic shared-memory limit is a per-function, process-wide attribute and one function serves every k (and
+    // every index of this dimension class): only ever raise it, to what the largest k needs.
+    {
+        static std::mutex attr_mu;
+        static std::unordered_map<const void*, size_t> attr_set;
+        std::lock_guard<std::mutex> g(attr_mu);
+        size_t& have = attr_set[reinterpret_cast<const void*>(fn)];
+        const size_t want = smem_for(CV_MAX_K);
+        if (have < want) {
+            CV_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(want)));
+            have = want;
+        }
+    }
     int occ = 0;
     CV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kScanThreads, smem));
     if (occ < 1) return fail(CV_ERR_CUDA, "scan kernel cannot be resident (smem=%zu)", smem);
@@ -313,7 +331,7 @@ int enqueue_query(cv_index* idx, QueryCtx* c, cudaStream_t stream, const float* 
     if (path == CV_PATH_AUTO) {
         // B = 1: fp32-exact K2 scan.  Batches: K3 on the tensor cores, except where K3 has no fast top-k
         // (k > 64 keeps lists in shared / global memory) and the batch is small enough for a few K2 passes.
-        const int auto_scan = nch <= 3 ? kAutoScanMaxBatchShortRows : kAutoScanMaxBatch;
+        const int auto_scan = nch <= 6 ? kAutoScanMaxBatchShortRows : kAutoScanMaxBatch;
         const bool scan = B <= std::min(max_qb, auto_scan) || !mma_supported(idx->Dp) ||
                           (k > 64 && max_qb > 0 && B <= 4 * max_qb);
         path = scan ? CV_PATH_SCAN : CV_PATH_MMA;
@@ -340,6 +358,8 @@ int enqueue_query(cv_index* idx, QueryCtx* c, cudaStream_t stream, const float* 
         m.Dp = idx->Dp;
         m.cosine = idx->cfg.metric == CV_METRIC_COSINE;
         m.row_offset = static_cast<uint32_t>(idx->cfg.row_offset);
+        m.row_stride = static_cast<uint32_t>(idx->row_stride);
+        m.precision = p->precision;
         m.q = d_q;
         m.B = B;
         m.k = k;
@@ -386,6 +406,7 @@ int enqueue_query(cv_index* idx, QueryCtx* c, cudaStream_t stream, const float* 
             a.q = d_q + static_cast<size_t>(done) * idx->D;
             a.k = k;
             a.row_offset = static_cast<uint32_t>(idx->cfg.row_offset);
+            a.row_stride = static_cast<uint32_t>(idx->row_stride);
             a.partial = c->d_partial.p;
             a.counter = c->d_counter;
             a.heads = c->d_heads;
@@ -455,6 +476,8 @@ int check_query_params(const cv_index* idx, const void* q, const cv_query_params
     if (p->k < 1 || p->k > CV_MAX_K) return fail(CV_ERR_INVALID, "k must be in [1, %d] (got %d)", CV_MAX_K, p->k);
     if (p->path < CV_PATH_AUTO || p->path > CV_PATH_MMA_2CTA)
         return fail(CV_ERR_INVALID, "unknown path %d", p->path);
+    if (p->precision < CV_PRECISION_AUTO || p->precision > CV_PRECISION_SPLIT)
+        return fail(CV_ERR_INVALID, "unknown precision %d", p->precision);
     return CV_OK;
 }
 
@@ -487,8 +510,8 @@ int cv_create(const cv_config* cfg, cv_index** out) {
     if (cfg->dim < 1 || cfg->dim > CV_MAX_DIM) return fail(CV_ERR_INVALID, "dim must be in [1, %d] (got %d)", CV_MAX_DIM, cfg->dim);
     if (cfg->metric != CV_METRIC_COSINE && cfg->metric != CV_METRIC_IP)
         return fail(CV_ERR_UNSUPPORTED, "unsupported metric %d (cosine and ip only)", cfg->metric);
-    if (cfg->capacity_rows < 0 || cfg->max_rows < 0 || cfg->row_offset < 0)
-        return fail(CV_ERR_INVALID, "negative capacity / max_rows / row_offset");
+    if (cfg->capacity_rows < 0 || cfg->max_rows < 0 || cfg->row_offset < 0 || cfg->row_stride < 0)
+        return fail(CV_ERR_INVALID, "negative capacity / max_rows / row_offset / row_stride");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -514,8 +537,11 @@ int cv_create(const cv_config* cfg, cv_index** out) {
     idx->sm_count = prop.multiProcessorCount;
     idx->max_rows = cfg->max_rows > 0 ? cfg->max_rows : (int64_t(1) << 28);
     if (cfg->capacity_rows > idx->max_rows) idx->max_rows = cfg->capacity_rows;
-    if (cfg->row_offset + idx->max_rows > (int64_t(1) << 32) - 1)
-        return fail(CV_ERR_INVALID, "row_offset + max_rows exceeds the 32-bit global row space");
+    idx->row_stride = cfg->row_stride > 0 ? cfg->row_stride : 1;
+    if (idx->row_stride > 1 && idx->max_rows > ((int64_t(1) << 32) - 2 - cfg->row_offset) / idx->row_stride)
+        idx->max_rows = ((int64_t(1) << 32) - 2 - cfg->row_offset) / idx->row_stride;  // default reservation of a striped shard
+    if (cfg->row_offset + (idx->max_rows - 1) * idx->row_stride > (int64_t(1) << 32) - 2)
+        return fail(CV_ERR_INVALID, "row_offset + max_rows * row_stride exceeds the 32-bit global row space");
 
     std::string err;
     if (!(err = idx->E.reserve(cfg->device, static_cast<size_t>(idx->max_rows) * idx->Dp * 2)).empty() ||
@@ -846,7 +872,7 @@ cudaError_t launch_merge_keys(const uint64_t* in, int G, int b_stride, int k_in,
 
 extern "C" {
 
-int cv_debug_mma_scores(cv_index* idx, const float* q, int32_t B, int32_t path, float* out_scores) {
+int cv_debug_mma_scores(cv_index* idx, const float* q, int32_t B, int32_t path, int32_t precision, float* out_scores) {
     if (!idx || !q || !out_scores || B < 1) return fail(CV_ERR_INVALID, "bad argument");
     if (path != CV_PATH_MMA && path != CV_PATH_MMA_1CTA && path != CV_PATH_MMA_2CTA)
         return fail(CV_ERR_INVALID, "path must be one of the tensor-core paths");
@@ -879,6 +905,7 @@ int cv_debug_mma_scores(cv_index* idx, const float* q, int32_t B, int32_t path, 
     p.label_code = CV_ANY;
     p.mask = nullptr;
     p.path = path;
+    p.precision = precision;
     rc = enqueue_query(idx, c, s, d_q.p, &p, nullptr, d_out.p, d_dump.p, n);
     if (rc) { (void)cudaStreamSynchronize(s); return rc; }
     CV_CUDA(cudaMemcpyAsync(out_scores, d_dump.p, sizeof(float) * B * n, cudaMemcpyDeviceToHost, s));

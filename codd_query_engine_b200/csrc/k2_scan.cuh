@@ -48,6 +48,7 @@ struct ScanArgs {
     const float* q;         // [QB][D] raw fp32 queries (device)
     int k;
     uint32_t row_offset;    // global row of local row 0
+    uint32_t row_stride;    // global row = row_offset + local row * row_stride
     uint64_t* partial;      // [QB][gridDim.x][k]
     unsigned int* counter;  // self-resetting "CTAs done" counter
     uint64_t* out;          // [QB][k] final keys (desc, 0 padded)
@@ -434,7 +435,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_topk(ScanArgs a) {
         }
         const float dot = reduce16<V>(acc, hl);
         const float score = dot * sc;
-        const uint64_t key = pack_key(score, a.row_offset + static_cast<uint32_t>(my_row));
+        const uint64_t key = pack_key(score, a.row_offset + static_cast<uint32_t>(my_row) * a.row_stride);
         {
             const uint64_t sb = s_bound[my_b];
             thr = sb > thr ? sb : thr;
@@ -673,7 +674,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_topk_wide(ScanArgs a) 
             for (int o = 16; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(kFullMask, acc[r], o);
             if (rows[r] >= 0) {  // warp-uniform
                 const float score = acc[r] * __ldg(a.scale + rows[r]);
-                const uint64_t key = pack_key(score, a.row_offset + static_cast<uint32_t>(rows[r]));
+                const uint64_t key = pack_key(score, a.row_offset + static_cast<uint32_t>(rows[r]) * a.row_stride);
                 if (key > thr) {
                     uint64_t kth;
                     if (warp_buf_append(my_list, cap, k, key, lane, cnt, kth) && kth > thr) thr = kth;

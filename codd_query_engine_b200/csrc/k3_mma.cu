@@ -25,6 +25,10 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <cstring>
+#include <mutex>
+#include <vector>
+
 #include "../../include/coddvec.h"
 #include "common.cuh"
 #include "k3_mma.cuh"
@@ -75,6 +79,21 @@ struct KArgs {
     float* dump;      // debug: [Bpad][dump_ld] scores, or nullptr
     int64_t dump_ld;
     uint64_t corpus_hint;
+    uint32_t row_stride;   // global row = row_offset + local row * row_stride (1 = dense block, G = cyclic shard)
+    // fused query preparation (q_resident only): the CTA normalises its 128 raw queries itself and writes the bf16
+    // tile (and, with `split`, the bf16 residual tile) straight into the swizzled shared-memory layout
+    const float* q_raw;    // [B][D] fp32 raw queries of this slice, or nullptr (the tile comes from tmap_q)
+    int D;
+    int cosine;
+    int split;             // 1: Q = hi + lo (two bf16 tiles, two MMAs per K step) -> fp32-accurate scores
+    // fused tail (k <= 64): survivors above the cross-CTA bound are appended to cand[q][...]; the last CTA of a
+    // query-tile group merges them, writes out[] and resets gthr / heads / cnt / done for the next launch
+    int fused_tail;
+    uint64_t* cand;        // [Bpad][cand_ld]
+    int cand_ld;           // P * k
+    uint32_t* cnt;         // [Bpad] survivors appended per query
+    uint32_t* done;        // [q_tiles * CG] CTAs of the group that have published
+    uint64_t* out;         // [B][k] final keys of this slice
 };
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
@@ -329,14 +348,13 @@ __device__ __forceinline__ uint32_t pick32(const uint32_t (&v)[32], int j) {
 
 // ------------------------------------------------------------------------------------------ query prep
 // Normalise fp32 queries exactly like the oracle (fp64 norm, fp32 divide), round to bf16, zero-pad to
-// [Bpad][Dp].  One warp per query row.
+// [Bpad][Dp].  One warp per query row.  Only the long-row mode (query tile streamed through the ring by TMA)
+// needs this launch; short rows build their tile inside k_mma_topk (prep_query_tile).
 __global__ void __launch_bounds__(128) k_prep_queries(const float* q, int B, int Bpad, int D, int Dp, int cosine,
-                                                      __nv_bfloat16* out, uint32_t* gthr, uint32_t* heads) {
+                                                      __nv_bfloat16* out) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (row >= Bpad) return;
-    if (lane == 0) gthr[row] = 0u;
-    for (int j = lane; j < kHeadsLd; j += 32) heads[static_cast<size_t>(row) * kHeadsLd + j] = 0u;
     __nv_bfloat16* o = out + static_cast<size_t>(row) * Dp;
     if (row >= B) {
         for (int d = lane; d < Dp; d += 32) o[d] = __float2bfloat16_rn(0.0f);
@@ -358,6 +376,73 @@ __global__ void __launch_bounds__(128) k_prep_queries(const float* q, int B, int
     for (int d = lane; d < Dp; d += 32) o[d] = __float2bfloat16_rn(d < D ? __fdiv_rn(r[d], safe) : 0.0f);
 }
 
+// Fused query preparation: the whole CTA turns its kQ raw fp32 queries into the bf16 UMMA operand tile in
+// shared memory -- normalised exactly like the oracle (fp64 norm, fp32 divide), rounded to bf16, laid out as the
+// TMA would have written it: K block kb = 16 KiB of [128 rows][64 elements], 128-byte rows, 16-byte chunk cc of
+// row r stored at chunk position cc ^ (r & 7) (SWIZZLE_128B; block bases are 1024-byte aligned).  With `split`
+// a second tile holds bf16(qhat - hi): hi + lo carries 16 mantissa bits, so the two MMAs per K step reproduce
+// the fp32 query to ~2^-17 relative.  Rows past B and elements past D are zero.  One warp per row; lane l owns
+// the 16-byte chunks l and l + 32 (rows of up to 512 elements stay resident, see mma_enqueue).
+__device__ __forceinline__ void prep_query_tile(unsigned char* sm_q, const float* q_raw, int q_row0, int B, int D,
+                                                int kblocks, int cosine, int split) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nchunks = kblocks * 8;
+    const bool vec = (D & 3) == 0 && (reinterpret_cast<uintptr_t>(q_raw) & 15) == 0;
+    for (int r = warp; r < kQ; r += kThreads / 32) {
+        const int qg = q_row0 + r;
+        const bool live = qg < B;  // warp-uniform
+        const float* src = q_raw + static_cast<size_t>(live ? qg : 0) * D;
+        float x[2][8];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int d0 = (lane + 32 * j) * 8;
+            if (live && vec && d0 + 8 <= D) {
+                const float4 u = __ldg(reinterpret_cast<const float4*>(src + d0));
+                const float4 w = __ldg(reinterpret_cast<const float4*>(src + d0 + 4));
+                x[j][0] = u.x; x[j][1] = u.y; x[j][2] = u.z; x[j][3] = u.w;
+                x[j][4] = w.x; x[j][5] = w.y; x[j][6] = w.z; x[j][7] = w.w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) x[j][e] = (live && d0 + e < D) ? __ldg(src + d0 + e) : 0.0f;
+            }
+        }
+        float safe = 1.0f;
+        if (cosine && live) {
+            double ss = 0.0;
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) ss += static_cast<double>(x[j][e]) * static_cast<double>(x[j][e]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(kFullMask, ss, o);
+            const float nrm = static_cast<float>(sqrt(ss));
+            safe = nrm > 0.0f ? nrm : 1.0f;
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int c = lane + 32 * j;
+            if (c < nchunks) {
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float v0 = __fdiv_rn(x[j][2 * e], safe), v1 = __fdiv_rn(x[j][2 * e + 1], safe);
+                    const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+                    hi[e] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+                    const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
+                    const __nv_bfloat16 l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
+                    lo[e] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
+                }
+                const int kb = c >> 3, cc = c & 7;
+                unsigned char* dst = sm_q + static_cast<size_t>(kb) * kBlockBytes + r * 128 + ((cc ^ (r & 7)) << 4);
+                *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                if (split)
+                    *reinterpret_cast<uint4*>(dst + static_cast<size_t>(kblocks) * kBlockBytes) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+        }
+    }
+    fence_proxy_async();  // generic-proxy stores above -> visible to the tensor core's async-proxy reads
+}
+
 // ------------------------------------------------------------------------------------------ main kernel
 // CG = 1: one CTA per SM works alone (M = 128 queries, N = 128 corpus rows per tile).
 // CG = 2: a CTA pair (cluster of 2, `cta_group::2`) shares every MMA: M = 256 queries (128 per CTA),
@@ -374,13 +459,14 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
     constexpr uint32_t kCols = kAccStages * TN;        // TMEM columns: 256 (CG=1) / 512 (CG=2)
     extern __shared__ __align__(1024) unsigned char smem[];
     // carve-up (all block bases 1024-byte aligned, as SWIZZLE_128B requires)
-    // q_resident: [query tile: kblocks x 16 KiB][ring: stages x 16 KiB corpus blocks]
+    // q_resident: [query tile: kblocks (x2 when split) x 16 KiB][ring: stages x 16 KiB corpus blocks]
     // streamed:   [ring: stages x (16 KiB query block + 16 KiB corpus block)]
     const bool qres = a.q_resident != 0;
     const int kStages = a.stages;
     const uint32_t stage_bytes = qres ? kBlockBytes : 2 * kBlockBytes;
     unsigned char* sm_q = smem;
-    unsigned char* sm_ring = smem + (qres ? static_cast<size_t>(a.kblocks) * kBlockBytes : 0);
+    const int qblocks = a.kblocks * (a.split ? 2 : 1);  // resident query tile: hi blocks, then the residual (lo) blocks
+    unsigned char* sm_ring = smem + (qres ? static_cast<size_t>(qblocks) * kBlockBytes : 0);
     float* sm_scale = reinterpret_cast<float*>(sm_ring + static_cast<size_t>(kStages) * stage_bytes);  // [2][TN]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm_scale + kAccStages * TN);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1 + 2 * kAccStages);
@@ -413,18 +499,21 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
         fence_proxy_async();
     }
     if (warp == 1) tmem_alloc<CG>(smem_u32(tmem_slot), kCols);
+    const bool fused_prep = a.q_raw != nullptr;  // (q_resident only)
+    if (fused_prep)
+        prep_query_tile(sm_q, a.q_raw, (qt * CG + static_cast<int>(rank)) * kQ, a.B, a.D, a.kblocks, a.cosine, a.split);
     tc_fence_before();
-    if (CG == 2) cluster_sync(); else __syncthreads();
+    if (CG == 2) cluster_sync(); else __syncthreads();  // barriers, TMEM address and both CTAs' query tiles are ready
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         // ===================================================================== TMA producer (every CTA)
         if (lane == 0) {
-            tma_prefetch_desc(&tmap_q);
+            if (!fused_prep) tma_prefetch_desc(&tmap_q);
             tma_prefetch_desc(&tmap_e);
             const int q_row = (qt * CG + static_cast<int>(rank)) * kQ;
-            if (qres) {
+            if (qres && !fused_prep) {
                 const uint32_t q_bytes = static_cast<uint32_t>(a.kblocks) * kBlockBytes;
                 if (rank == 0) mbar_arrive_expect_tx(bar_q, q_bytes * CG);
                 else mbar_arrive_cluster(bar_q, 0);
@@ -454,7 +543,7 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
         // ===================================================================== MMA issuer (leader CTA only)
         if (lane == 0 && rank == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(kQ * CG, TN);
-            if (qres) {
+            if (qres && !fused_prep) {
                 mbar_wait(bar_q, 0);
                 tc_fence_after();
             }
@@ -474,6 +563,12 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
                     for (int ks = 0; ks < kKB / 16; ++ks)  // UMMA_K = 16 bf16 = 32 bytes inside the swizzle row
                         umma_bf16<CG>(tmem_d, umma_desc_sw128(a_addr + ks * 32), umma_desc_sw128(b_addr + ks * 32), idesc,
                                       (kb | ks) != 0 ? 1u : 0u);
+                    if (a.split) {  // + (residual query tile) x (the same corpus block)
+                        const uint32_t lo_addr = a_addr + static_cast<uint32_t>(a.kblocks) * kBlockBytes;
+#pragma unroll
+                        for (int ks = 0; ks < kKB / 16; ++ks)
+                            umma_bf16<CG>(tmem_d, umma_desc_sw128(lo_addr + ks * 32), umma_desc_sw128(b_addr + ks * 32), idesc, 1u);
+                    }
                     umma_commit<CG>(bar_empty + 8 * stage);  // frees the ring slot (in both CTAs) once read
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
@@ -486,7 +581,8 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
         const int et = threadIdx.x - 64;                 // 0..127
         const int qlane = 32 * (warp & 3) + lane;        // TMEM lane = query within this CTA's 128
         const int qglobal = (qt * CG + static_cast<int>(rank)) * kQ + qlane;
-        uint64_t* const glist = a.lists + (static_cast<size_t>(p) * a.Bpad + qglobal) * a.k;
+        const bool fused_tail = KREG > 0 && a.fused_tail != 0;
+        uint64_t* const glist = fused_tail ? nullptr : a.lists + (static_cast<size_t>(p) * a.Bpad + qglobal) * a.k;
         // large k (KREG == 0): the working list is in shared memory when it fits (fast warp-cooperative
         // insertion), else directly in global memory; lanes of a warp own consecutive lists either way
         uint64_t* list = (KREG == 0 && a.smem_lists) ? sm_lists + static_cast<size_t>(qlane) * a.k : glist;
@@ -551,7 +647,7 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
             mbar_wait(bar_tfull + 8 * as, aphase);
             tc_fence_after();
             const float* sc_tile = sm_scale + as * TN;
-            const uint32_t row0 = a.row_offset + static_cast<uint32_t>(t) * TN;
+            const uint32_t lrow0 = static_cast<uint32_t>(t) * TN;  // local row of the tile's first column
 #pragma unroll 1
             for (int c = 0; c < TN / 32; ++c) {
                 uint32_t v[32];
@@ -584,7 +680,7 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
                             cand &= cand - 1;
                             const float s = __uint_as_float(pick32(v, j));
                             if (s > thr) {  // thr may have risen since the bitmap was built
-                                list_insert_regs<KR>(L, pack_key(s, row0 + c * 32 + j));
+                                list_insert_regs<KR>(L, pack_key(s, a.row_offset + (lrow0 + c * 32 + j) * a.row_stride));
                                 if (L[KR - 1] != 0ull) thr_local = key_score(L[KR - 1]);
                                 thr = fmaxf(thr, thr_local);
                                 if (share && s > best_local) {  // publish this CTA's new head for the query
@@ -616,7 +712,8 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
                             cm &= cm - 1;
                             const float s = __shfl_sync(kFullMask, __uint_as_float(pick32(v, j)), src);
                             if (s > thr_src) {
-                                const uint64_t kth = warp_list_insert(lst, a.k, pack_key(s, row0 + c * 32 + j), lane);
+                                const uint64_t kth =
+                                    warp_list_insert(lst, a.k, pack_key(s, a.row_offset + (lrow0 + c * 32 + j) * a.row_stride), lane);
                                 if (kth != 0ull) local_src = key_score(kth);
                                 thr_src = fmaxf(thr_src, local_src);
                                 changed = true;
@@ -638,7 +735,69 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
             }
             if (++as == kAccStages) { as = 0; aphase ^= 1; }
         }
-        if (KREG > 0) {
+        if (fused_tail) {
+            // ---- fused tail: no merge launch.  P == 1: this list is final.  Otherwise publish the keys that can
+            // still be in the global top-k -- score >= max(largest k-th best any CTA reached, heads bound): both are
+            // lower bounds on the global k-th best score, so every global top-k key survives in its CTA -- to
+            // cand[q][...] (one atomicAdd per query reserves the range; ~k ln k keys per query in the whole grid),
+            // and let the last CTA of the group (threadfence + counter) merge its 128 queries, thread = query.
+            if (a.P == 1) {
+                if (live) {
+#pragma unroll
+                    for (int j = 0; j < KR; ++j)
+                        if (j >= KR - a.k) a.out[static_cast<size_t>(qglobal) * a.k + (j - (KR - a.k))] = L[j];
+                }
+            } else {
+                __shared__ int s_last;
+                const int group = qt * CG + static_cast<int>(rank);
+                if (live) {
+                    const uint32_t g = max(__ldcg(a.gthr + qglobal), heads_bound(head_row, a.P, a.k));
+                    int ns = 0;
+#pragma unroll
+                    for (int j = 0; j < KR; ++j)
+                        ns += (j >= KR - a.k && L[j] != 0ull && static_cast<uint32_t>(L[j] >> 32) >= g) ? 1 : 0;
+                    if (ns) {  // the list is sorted: the survivors are its first ns entries
+                        const uint32_t pos = atomicAdd(a.cnt + qglobal, static_cast<uint32_t>(ns));
+                        uint64_t* dst = a.cand + static_cast<size_t>(qglobal) * a.cand_ld + pos;
+#pragma unroll
+                        for (int j = 0; j < KR; ++j) {
+                            const int i = j - (KR - a.k);
+                            if (i >= 0 && i < ns) __stcg(dst + i, L[j]);
+                        }
+                    }
+                }
+                __threadfence();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (et == 0) s_last = atomicAdd(a.done + group, 1u) == static_cast<unsigned>(a.P - 1) ? 1 : 0;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (s_last) {
+                    __threadfence();
+                    if (live) {
+                        const uint32_t m = __ldcg(a.cnt + qglobal);
+                        const uint64_t* src = a.cand + static_cast<size_t>(qglobal) * a.cand_ld;
+#pragma unroll
+                        for (int j = 0; j < KR; ++j) L[j] = (j < KR - a.k) ? ~0ull : 0ull;
+#pragma unroll 1
+                        for (uint32_t i0 = 0; i0 < m; i0 += 8) {
+                            uint64_t kk[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) kk[u] = (i0 + u < m) ? __ldcg(src + i0 + u) : 0ull;
+#pragma unroll
+                            for (int u = 0; u < 8; ++u)
+                                if (kk[u] > L[KR - 1]) list_insert_regs<KR>(L, kk[u]);
+                        }
+#pragma unroll
+                        for (int j = 0; j < KR; ++j)
+                            if (j >= KR - a.k) a.out[static_cast<size_t>(qglobal) * a.k + (j - (KR - a.k))] = L[j];
+                        // every CTA of the group is done: leave the shared state zero for the next launch
+                        a.cnt[qglobal] = 0u;
+                        a.gthr[qglobal] = 0u;
+                        for (int v = 0; v < (a.P + 3) / 4; ++v) reinterpret_cast<uint4*>(head_row)[v] = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                    if (et == 0) a.done[group] = 0u;
+                }
+            }
+        } else if (KREG > 0) {
 #pragma unroll
             for (int j = 0; j < KR; ++j)
                 if (j >= KR - a.k) glist[j - (KR - a.k)] = L[j];
@@ -657,15 +816,16 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
 
 constexpr size_t kSmemLimit = 232448;  // 227 KiB: the per-CTA maximum on sm_100
 
-size_t mma_smem_bytes(int kblocks, int stages, int cg, size_t list_bytes, bool q_resident) {
-    const size_t blocks = q_resident ? static_cast<size_t>(kblocks + stages) : 2 * static_cast<size_t>(stages);
+// qblocks: 16 KiB blocks of the resident query tile (0 when the tile is streamed through the ring)
+size_t mma_smem_bytes(int qblocks, int stages, int cg, size_t list_bytes, bool q_resident) {
+    const size_t blocks = q_resident ? static_cast<size_t>(qblocks + stages) : 2 * static_cast<size_t>(stages);
     return blocks * kBlockBytes + kAccStages * kTN * cg * sizeof(float) +
            (2 * kMaxStages + 1 + 2 * kAccStages) * sizeof(uint64_t) + 16 + list_bytes;
 }
 
-int mma_stages(int kblocks, int cg, size_t list_bytes, bool q_resident) {
+int mma_stages(int qblocks, int cg, size_t list_bytes, bool q_resident) {
     int s = kMaxStages;
-    while (s > 1 && mma_smem_bytes(kblocks, s, cg, list_bytes, q_resident) > kSmemLimit) --s;
+    while (s > 1 && mma_smem_bytes(qblocks, s, cg, list_bytes, q_resident) > kSmemLimit) --s;
     return s;
 }
 
@@ -716,6 +876,27 @@ std::string& mma_error() { return g_mma_err; }
         }                                                                                               \
     } while (0)
 
+// The dynamic shared-memory limit is a per-function, process-wide attribute: raise it to the architectural maximum
+// once per kernel instead of setting it to each launch's need (a later, smaller setting would make a concurrent or
+// cached larger launch fail).
+int raise_smem_limit(MmaKernel kernel) {
+    static std::mutex mu;
+    static std::vector<MmaKernel> done;
+    std::lock_guard<std::mutex> g(mu);
+    for (MmaKernel k : done)
+        if (k == kernel) return 0;
+    MMA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemLimit)));
+    done.push_back(kernel);
+    return 0;
+}
+
+// Self-resetting cross-CTA state for `queries` queries: heads [q][kHeadsLd], gthr [q], cnt [q], done [q / kQ + 1].
+// All of it is zero between launches (the fused tail's last CTA per group clears what its group dirtied), so it is
+// zeroed once, when (re)allocated.
+size_t mma_state_bytes(int queries) {
+    return (static_cast<size_t>(queries) * (kHeadsLd + 2) + static_cast<size_t>(queries) / kQ + 4) * sizeof(uint32_t);
+}
+
 int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* launches) {
     if (!mma_supported(m.Dp))
         return mma_fail(CV_ERR_UNSUPPORTED, "tensor-core path supports padded dim <= 4096 (got " + std::to_string(m.Dp) + ")");
@@ -726,19 +907,35 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
     const int tile_rows = kTN * cg, tile_q = kQ * cg;
     const int n_tiles = static_cast<int>((m.n + tile_rows - 1) / tile_rows);
     const int units = m.sm_count / cg;  // CTAs or CTA pairs that fit the chip
-    // k > 32: per-query lists go to shared memory if a >= 3-stage ring still fits beside them
+    // Query precision.  bf16 queries carry an error of up to 2^-9 * sum|q_i c_i| per score: ~1e-4 on dense rows of
+    // >= 128 dimensions, but up to 2^-8 on very short or sparse ones -- outside the 1e-3 the north star allows.  Rows
+    // of up to 128 padded elements therefore take the hi/lo split by default (two bf16 tiles, two MMAs per K step:
+    // ~2^-17 relative, and the scan is HBM-bound there anyway); CV_PRECISION_SPLIT asks for it at any dimension whose
+    // double tile still fits shared memory.
+    bool split = m.precision == CV_PRECISION_SPLIT || (m.precision == CV_PRECISION_AUTO && m.Dp <= 128);
+    if (split && mma_smem_bytes(2 * kblocks, 2, cg, 0, true) > kSmemLimit) {
+        if (m.precision == CV_PRECISION_SPLIT)
+            return mma_fail(CV_ERR_UNSUPPORTED, "split-precision queries need the double query tile resident in shared memory: "
+                                                "dim <= 384 (got " + std::to_string(m.Dp) + ")");
+        split = false;
+    }
+    const int qblocks = kblocks * (split ? 2 : 1);
+    // k > 64: per-query lists go to shared memory if a >= 3-stage ring still fits beside them
     size_t smem_list_bytes = m.k > 64 && !m.dump ? static_cast<size_t>(kQ) * m.k * sizeof(uint64_t) : 0;
     // Short rows keep the query tile resident (a deep corpus-only ring); long rows stream the query's K
     // blocks through the ring with the corpus blocks (7 x 32 KiB stages) -- the tile would crowd the ring out.
-    bool q_resident = mma_smem_bytes(kblocks, 6, cg, 0, true) <= kSmemLimit;
-    if (smem_list_bytes && mma_smem_bytes(kblocks, 3, cg, smem_list_bytes, q_resident) > kSmemLimit) smem_list_bytes = 0;
-    const int stages = mma_stages(kblocks, cg, smem_list_bytes, q_resident);
-    const size_t smem = mma_smem_bytes(kblocks, stages, cg, smem_list_bytes, q_resident);
+    const bool q_resident = split || mma_smem_bytes(kblocks, 6, cg, 0, true) <= kSmemLimit;
+    if (smem_list_bytes && mma_smem_bytes(qblocks, 3, cg, smem_list_bytes, q_resident) > kSmemLimit) smem_list_bytes = 0;
+    const int stages = mma_stages(qblocks, cg, smem_list_bytes, q_resident);
+    const size_t smem = mma_smem_bytes(qblocks, stages, cg, smem_list_bytes, q_resident);
     if (smem > kSmemLimit)
         return mma_fail(CV_ERR_UNSUPPORTED, "tensor-core path: query tile does not fit shared memory at dim " + std::to_string(m.Dp));
+    const bool fused_prep = q_resident && kblocks <= 8;     // prep_query_tile: lanes own chunks l and l + 32
+    const bool fused_tail = m.k <= 64 && m.dump == nullptr;  // register-resident lists
     MmaKernel kernel = cg == 2 ? pick_mma_kernel<2>(m.dump != nullptr, m.k) : pick_mma_kernel<1>(m.dump != nullptr, m.k);
-    MMA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    // batches larger than one wave of query tiles are processed in slices
+    int rc;
+    if ((rc = raise_smem_limit(kernel))) return rc;
+    // batches larger than one wave of query tiles are processed in slices (stream order keeps the scratch safe)
     int done = 0;
     while (done < m.B) {
         const int Bs = std::min(m.B - done, units * tile_q);
@@ -747,33 +944,44 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
         int P = units / QT;
         if (P > n_tiles) P = n_tiles;
         if (P < 1) P = 1;
-        // scratch: [Qb bf16 Bpad x Dp][shared thresholds Bpad u32][lists P x Bpad x k u64]
-        const size_t q_bytes = (static_cast<size_t>(Bpad) * m.Dp * 2 + 1023) / 1024 * 1024;
-        const size_t thr_bytes = (static_cast<size_t>(Bpad) * sizeof(uint32_t) * (1 + kHeadsLd) + 1023) / 1024 * 1024;
+        // work scratch (contents do not matter between launches): [bf16 queries Bpad x Dp (long rows only)][keys Bpad x P x k]
+        const size_t q_bytes = fused_prep ? 0 : (static_cast<size_t>(Bpad) * m.Dp * 2 + 1023) / 1024 * 1024;
         const size_t list_bytes = static_cast<size_t>(P) * Bpad * m.k * sizeof(uint64_t);
-        const size_t need = q_bytes + thr_bytes + list_bytes;
+        const size_t need = q_bytes + list_bytes;
         if (need > scratch.cap) {
-            if (scratch.p) {
-                MMA_CUDA(cudaStreamSynchronize(m.stream));
-                cudaFree(scratch.p);
-                scratch.p = nullptr;
-                scratch.cap = 0;
-            }
+            MMA_CUDA(cudaStreamSynchronize(m.stream));
+            if (scratch.p) cudaFree(scratch.p);
+            scratch.p = nullptr;
+            scratch.cap = 0;
             MMA_CUDA(cudaMalloc(&scratch.p, need + need / 2));
             scratch.cap = need + need / 2;
         }
+        if (Bpad > scratch.state_q) {
+            MMA_CUDA(cudaStreamSynchronize(m.stream));
+            if (scratch.state) cudaFree(scratch.state);
+            scratch.state = nullptr;
+            scratch.state_q = 0;
+            const int cap_q = std::max(Bpad, 1024);
+            MMA_CUDA(cudaMalloc(&scratch.state, mma_state_bytes(cap_q)));
+            MMA_CUDA(cudaMemsetAsync(scratch.state, 0, mma_state_bytes(cap_q), m.stream));
+            scratch.state_q = cap_q;
+        }
         __nv_bfloat16* qb = reinterpret_cast<__nv_bfloat16*>(scratch.p);
-        uint32_t* heads = reinterpret_cast<uint32_t*>(scratch.p + q_bytes);   // [Bpad][kHeadsLd], 16-byte aligned rows
-        uint32_t* gthr = heads + static_cast<size_t>(Bpad) * kHeadsLd;           // [Bpad]
-        uint64_t* lists = reinterpret_cast<uint64_t*>(scratch.p + q_bytes + thr_bytes);
-
-        k_prep_queries<<<(Bpad + 3) / 4, 128, 0, m.stream>>>(m.q + static_cast<size_t>(done) * m.D, Bs, Bpad, m.D, m.Dp,
-                                                             m.cosine ? 1 : 0, qb, gthr, heads);
-        MMA_CUDA(cudaGetLastError());
+        uint64_t* lists = reinterpret_cast<uint64_t*>(scratch.p + q_bytes);
+        uint32_t* heads = reinterpret_cast<uint32_t*>(scratch.state);                    // [state_q][kHeadsLd], 16-byte aligned rows
+        uint32_t* gthr = heads + static_cast<size_t>(scratch.state_q) * kHeadsLd;         // [state_q]
+        uint32_t* cnt = gthr + scratch.state_q;                                           // [state_q]
+        uint32_t* group_done = cnt + scratch.state_q;                                     // [state_q / kQ]
 
         CUtensorMap tq, te;
-        int rc;
-        if ((rc = encode_map(&tq, qb, m.Dp, Bpad, kQ))) return rc;
+        memset(&tq, 0, sizeof(tq));
+        if (!fused_prep) {
+            k_prep_queries<<<(Bpad + 3) / 4, 128, 0, m.stream>>>(m.q + static_cast<size_t>(done) * m.D, Bs, Bpad, m.D, m.Dp,
+                                                                 m.cosine ? 1 : 0, qb);
+            MMA_CUDA(cudaGetLastError());
+            if (launches) launches->fetch_add(1);
+            if ((rc = encode_map(&tq, qb, m.Dp, Bpad, kQ))) return rc;
+        }
         if ((rc = encode_map(&te, m.E, m.Dp, static_cast<uint64_t>(m.n), kTN))) return rc;
 
         KArgs a;
@@ -789,6 +997,7 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
         a.q_resident = q_resident ? 1 : 0;
         a.k = m.k;
         a.row_offset = m.row_offset;
+        a.row_stride = m.row_stride ? m.row_stride : 1u;
         a.n_tiles = n_tiles;
         a.q_tiles = QT;
         a.P = P;
@@ -801,6 +1010,16 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
         a.dump = m.dump ? m.dump + static_cast<size_t>(done) * m.dump_ld : nullptr;
         a.dump_ld = m.dump_ld;
         a.corpus_hint = QT > 1 ? kEvictNormal : kEvictFirst;
+        a.q_raw = fused_prep ? m.q + static_cast<size_t>(done) * m.D : nullptr;
+        a.D = m.D;
+        a.cosine = m.cosine ? 1 : 0;
+        a.split = split ? 1 : 0;
+        a.fused_tail = fused_tail ? 1 : 0;
+        a.cand = lists;
+        a.cand_ld = P * m.k;
+        a.cnt = cnt;
+        a.done = group_done;
+        a.out = m.out + static_cast<size_t>(done) * m.k;
 
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(static_cast<unsigned>(QT * P * cg));
@@ -815,11 +1034,16 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         MMA_CUDA(cudaLaunchKernelEx(&cfg, kernel, tq, te, a));
-        MMA_CUDA(launch_merge_keys(lists, P, Bpad, m.k, m.k, m.out + static_cast<size_t>(done) * m.k, Bs, m.stream,
-                                   P > 1 && !m.dump ? gthr : nullptr));
-        if (launches) launches->fetch_add(3);
+        if (launches) launches->fetch_add(1);
+        if (!fused_tail) {
+            // k > 64 / score dump: per-CTA lists [P][Bpad][k] -> K4, then clear the thresholds the scan left behind
+            MMA_CUDA(launch_merge_keys(lists, P, Bpad, m.k, m.k, m.out + static_cast<size_t>(done) * m.k, Bs, m.stream,
+                                       P > 1 && !m.dump ? gthr : nullptr));
+            MMA_CUDA(cudaMemsetAsync(heads, 0, static_cast<size_t>(Bpad) * kHeadsLd * sizeof(uint32_t), m.stream));
+            MMA_CUDA(cudaMemsetAsync(gthr, 0, static_cast<size_t>(Bpad) * sizeof(uint32_t), m.stream));
+            if (launches) launches->fetch_add(1);
+        }
         done += Bs;
-        if (done < m.B) MMA_CUDA(cudaStreamSynchronize(m.stream));  // scratch is reused by the next slice
     }
     return 0;
 }

@@ -8,8 +8,10 @@
 namespace cv {
 
 struct MmaScratch {  // device scratch owned by the query context, grown on demand
-    unsigned char* p = nullptr;
+    unsigned char* p = nullptr;      // work area: bf16 queries (long rows) + candidate keys; contents do not matter between launches
     size_t cap = 0;
+    unsigned char* state = nullptr;  // cross-CTA thresholds / counters for state_q queries: zero between launches (self-resetting)
+    int state_q = 0;
 };
 
 struct MmaArgs {
@@ -23,6 +25,8 @@ struct MmaArgs {
     int D, Dp;
     bool cosine;
     uint32_t row_offset;
+    uint32_t row_stride;    // global row = row_offset + local row * row_stride (0 / 1 = dense)
+    int precision;          // CV_PRECISION_*
     const float* q;         // [B][D] fp32 raw (device)
     int B, k;
     uint64_t* out;          // [B][k]

@@ -35,6 +35,10 @@ PATH_MMA = 2
 PATH_MMA_1CTA = 3
 PATH_MMA_2CTA = 4
 
+PRECISION_AUTO = 0   # bf16 queries; hi/lo split on rows of up to 128 padded elements
+PRECISION_BF16 = 1
+PRECISION_SPLIT = 2  # hi/lo split (fp32-accurate scores) wherever the double query tile fits (dim <= 384)
+
 LIB_NAME = "libcoddvec.so"
 
 
@@ -55,6 +59,7 @@ class _Config(ctypes.Structure):
         ("capacity_rows", ctypes.c_int64),
         ("max_rows", ctypes.c_int64),
         ("row_offset", ctypes.c_int64),
+        ("row_stride", ctypes.c_int64),
     ]
 
 
@@ -66,7 +71,7 @@ class _QueryParams(ctypes.Structure):
         ("label_code", ctypes.c_uint32),
         ("mask", ctypes.c_void_p),
         ("path", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("precision", ctypes.c_int32),
     ]
 
 
@@ -134,7 +139,7 @@ def load_library() -> ctypes.CDLL:
         "cv_encode_key": (u64, [ctypes.c_float, u32]),
         "cv_get_rows": (ctypes.c_int, [vp, vp, i64, vp, vp, vp, vp]),
         "cv_load_rows": (ctypes.c_int, [vp, vp, vp, vp, vp, i64, vp]),
-        "cv_debug_mma_scores": (ctypes.c_int, [vp, vp, i32, i32, vp]),
+        "cv_debug_mma_scores": (ctypes.c_int, [vp, vp, i32, i32, i32, vp]),
         "cv_count": (i64, [vp]),
         "cv_dim": (i32, [vp]),
         "cv_set_profiling": (ctypes.c_int, [vp, i32]),
@@ -225,15 +230,17 @@ class NativeIndex:
     """One device-resident shard: bf16 rows + scale + namespace/label codes on one B200."""
 
     def __init__(self, dim: int, metric: int = METRIC_COSINE, device: int = 0, capacity_rows: int = 0,
-                 max_rows: int = 0, row_offset: int = 0):
+                 max_rows: int = 0, row_offset: int = 0, row_stride: int = 1):
         self._lib = load_library()
         self._h = ctypes.c_void_p()
-        cfg = _Config(int(dim), int(metric), int(device), 0, int(capacity_rows), int(max_rows), int(row_offset))
+        cfg = _Config(int(dim), int(metric), int(device), 0, int(capacity_rows), int(max_rows), int(row_offset),
+                      int(row_stride))
         _check(self._lib.cv_create(ctypes.byref(cfg), ctypes.byref(self._h)))
         self.dim = int(dim)
         self.metric = int(metric)
         self.device = int(device)
         self.row_offset = int(row_offset)
+        self.row_stride = int(row_stride) or 1
 
     # -- lifecycle
     def close(self) -> None:
@@ -293,7 +300,7 @@ class NativeIndex:
 
     # -- K2 / K3 / K4
     def query(self, queries: np.ndarray, k: int, ns_code: int = ANY, label_code: int = ANY, mask=None,
-              path: int = PATH_AUTO):
+              path: int = PATH_AUTO, precision: int = PRECISION_AUTO):
         """Host API.  Returns (scores [B][k] fp32 desc, rows [B][k] int64 global (-1 pad), counts [B])."""
         q = np.ascontiguousarray(queries, dtype=np.float32)
         if q.ndim == 1:
@@ -307,7 +314,8 @@ class NativeIndex:
             need = (len(self) + 31) // 32
             if m.ndim != 1 or m.shape[0] < need:
                 raise ValueError(f"mask needs {need} uint32 words, got shape {m.shape}")
-        p = _QueryParams(B, int(k), int(ns_code), int(label_code), None if m is None else m.ctypes.data, int(path), 0)
+        p = _QueryParams(B, int(k), int(ns_code), int(label_code), None if m is None else m.ctypes.data, int(path),
+                         int(precision))
         scores = np.empty((B, int(k) if k > 0 else 0), dtype=np.float32)
         rows = np.empty((B, int(k) if k > 0 else 0), dtype=np.int64)
         counts = np.empty(B, dtype=np.int32)
@@ -315,12 +323,12 @@ class NativeIndex:
         return scores, rows, counts
 
     def query_device(self, q_ptr: int, B: int, k: int, out_keys_ptr: int, ns_code: int = ANY, label_code: int = ANY,
-                     mask_ptr: int = 0, path: int = PATH_AUTO, stream=None) -> None:
+                     mask_ptr: int = 0, path: int = PATH_AUTO, stream=None, precision: int = PRECISION_AUTO) -> None:
         """Asynchronous device-resident API: enqueue on `stream`, no sync.
 
         stream: None = the index's own stream; otherwise a cudaStream_t handle such as
         torch.cuda.current_stream().cuda_stream (0 = the default stream)."""
-        p = _QueryParams(int(B), int(k), int(ns_code), int(label_code), mask_ptr or None, int(path), 0)
+        p = _QueryParams(int(B), int(k), int(ns_code), int(label_code), mask_ptr or None, int(path), int(precision))
         _check(self._lib.cv_query_device(self._h, q_ptr, ctypes.byref(p), out_keys_ptr, _stream_arg(stream)))
 
     def query_device_exchange(self, q_ptr: int, B: int, k: int, out_keys_ptr: int, px: _PeerExchange, seq: int,
@@ -361,11 +369,11 @@ class NativeIndex:
         _check(self._lib.cv_get_rows(self._h, _ptr(r), n, _ptr(vec), _ptr(scale), _ptr(ns), _ptr(lb)))
         return vec, scale, ns, lb
 
-    def debug_mma_scores(self, queries: np.ndarray, path: int = PATH_MMA) -> np.ndarray:
+    def debug_mma_scores(self, queries: np.ndarray, path: int = PATH_MMA, precision: int = PRECISION_AUTO) -> np.ndarray:
         """Every score the tensor-core path computes: [B][count] fp32 (testing aid)."""
         q = np.ascontiguousarray(queries, dtype=np.float32)
         out = np.empty((q.shape[0], len(self)), dtype=np.float32)
-        _check(self._lib.cv_debug_mma_scores(self._h, _ptr(q), q.shape[0], int(path), _ptr(out)))
+        _check(self._lib.cv_debug_mma_scores(self._h, _ptr(q), q.shape[0], int(path), int(precision), _ptr(out)))
         return out
 
     def set_profiling(self, enabled: bool) -> None:

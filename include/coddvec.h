@@ -59,6 +59,13 @@ extern "C" {
 #define CV_PATH_MMA_1CTA 3 /* K3 forced to single-CTA tiles (cta_group::1, 128 queries x 128 rows) */
 #define CV_PATH_MMA_2CTA 4 /* K3 forced to CTA pairs (cta_group::2, 256 queries x 256 rows) */
 
+/* Query precision of the tensor-core path (K2 always scores with the fp32 query).  AUTO: bf16 queries, except on
+ * rows of up to 128 padded elements, where the hi/lo split (two bf16 tiles, two MMAs per K step, ~2^-17 relative)
+ * keeps every score within the 1e-3 the north star allows. */
+#define CV_PRECISION_AUTO 0
+#define CV_PRECISION_BF16 1  /* one bf16 query tile at every dimension */
+#define CV_PRECISION_SPLIT 2 /* hi/lo split at every dimension whose double tile fits shared memory (dim <= 384) */
+
 typedef struct cv_index cv_index;
 
 typedef struct cv_config {
@@ -69,6 +76,8 @@ typedef struct cv_config {
     int64_t capacity_rows; /* rows to back with physical memory up front (0 = grow on demand) */
     int64_t max_rows;      /* virtual reservation: hard upper bound on rows (0 = 2^28) */
     int64_t row_offset;    /* global row number of local row 0 */
+    int64_t row_stride;    /* global row = row_offset + local row * row_stride; 0 or 1 = a dense block (row-sharded
+                              SPMD use), G = this index holds every G-th row of a collection striped over G devices */
 } cv_config;
 
 typedef struct cv_query_params {
@@ -79,7 +88,7 @@ typedef struct cv_query_params {
     const uint32_t* mask; /* NULL or ceil(count/32) words, bit (r & 31) of word r>>5 set => row r eligible;
                              shared by the whole batch; host memory for cv_query, device memory for cv_query_device */
     int32_t path;         /* CV_PATH_* */
-    int32_t reserved;
+    int32_t precision;    /* CV_PRECISION_* (0 = AUTO) */
 } cv_query_params;
 
 typedef struct cv_stats_t {
@@ -167,8 +176,8 @@ int cv_load_rows(cv_index* idx, const uint16_t* bf16, const float* scale, const 
 
 /* Testing aid: run the tensor-core path (K3) for B queries and return EVERY score it computed,
  * out_scores[B][count] (host), so that tests can compare the whole score matrix with the oracle.
- * path: CV_PATH_MMA, CV_PATH_MMA_1CTA or CV_PATH_MMA_2CTA. */
-int cv_debug_mma_scores(cv_index* idx, const float* q, int32_t B, int32_t path, float* out_scores);
+ * path: CV_PATH_MMA, CV_PATH_MMA_1CTA or CV_PATH_MMA_2CTA; precision: CV_PRECISION_*. */
+int cv_debug_mma_scores(cv_index* idx, const float* q, int32_t B, int32_t path, int32_t precision, float* out_scores);
 
 int64_t cv_count(const cv_index* idx);
 int32_t cv_dim(const cv_index* idx);

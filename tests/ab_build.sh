@@ -7,7 +7,8 @@ set -euo pipefail
 ref=${1:?usage: tests/ab_build.sh <git-ref>}
 root=$(cd "$(dirname "$0")/.." && pwd)
 name=$(echo "$ref" | tr '/' '_')
-tmp=$(mktemp -d /tmp/ab_tree.XXXXXX)
+mkdir -p "$root/build/wt"
+tmp=$(mktemp -d "$root/build/wt/ab_tree.XXXXXX")
 git -C "$root" worktree add -f --detach "$tmp" "$ref" > /dev/null
 ( cd "$tmp" && python -m codd_query_engine_b200.build > /dev/null )
 mkdir -p "$root/ab_libs"

@@ -39,8 +39,8 @@ def check_topk(got_scores, got_rows, got_counts, full_scores, eligible, k, tol, 
         assert (keys[:-1] > keys[1:]).all(), f"query {b}: not ordered by (score desc, row asc)"
         # set equality modulo near-ties around the k-th oracle score
         okeys = bf.pack_keys(np.where(elig, sc, -np.inf), np.arange(n))
-        order = np.argsort(okeys)[::-1]
-        order = order[elig[order]][:want]
+        top = np.argpartition(okeys, n - want)[n - want:]  # the `want` largest keys (ineligible rows sit at -inf) ...
+        order = top[np.argsort(okeys[top])[::-1]]           # ... in (score desc, row asc) order
         if exact_rows:
             assert rows.tolist() == order.tolist(), f"query {b}: rows {rows} != oracle {order}"
         kth = sc[order[-1]]

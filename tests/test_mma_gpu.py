@@ -26,11 +26,19 @@ def build(native, n, D, seed, metric=bf.METRIC_COSINE, **kw):
     return idx, vec, scale, rng
 
 
-def bf16_query_scores(stored, scale, q, metric=bf.METRIC_COSINE):
-    """What K3 computes exactly: the normalised query rounded to bf16, fp32 accumulate."""
+def bf16_query_scores(stored, scale, q, metric=bf.METRIC_COSINE, split=None):
+    """What K3 computes exactly: the normalised query rounded to bf16, fp32 accumulate -- plus, on rows of up to
+    128 padded elements (CV_PRECISION_AUTO) or when asked for (CV_PRECISION_SPLIT), the bf16 residual of the query
+    through a second MMA."""
     qhat = bf.normalise_query(q, metric)
-    qb = bf.bf16_bits_to_f32(bf.f32_to_bf16_bits(qhat))
-    return bf.scores_fp32(stored, scale, qb)
+    hi = bf.bf16_bits_to_f32(bf.f32_to_bf16_bits(qhat))
+    out = bf.scores_fp32(stored, scale, hi)
+    if split is None:
+        split = -(-stored.shape[1] // 64) * 64 <= 128
+    if split:
+        lo = bf.bf16_bits_to_f32(bf.f32_to_bf16_bits(qhat - hi))
+        out = out + bf.scores_fp32(stored, scale, lo)
+    return out
 
 
 VARIANTS = ["1cta", "2cta"]
@@ -81,9 +89,10 @@ def test_mma_and_scan_paths_agree(native):
     q = rng.standard_normal((4, 384)).astype(np.float32)
     s1, r1, c1 = idx.query(q, 10, path=native.PATH_SCAN)
     s2, r2, c2 = idx.query(q, 10, path=native.PATH_MMA)
-    assert np.array_equal(c1, c2) and np.abs(s1 - s2).max() <= TOL
-    same = (r1 == r2).mean()
-    assert same > 0.9  # random data: near-ties within 1e-3 are rare
+    full = oracle_full_scores(stored, scale, q)
+    check_topk(s1, r1, c1, full, None, 10, tol=2e-6)
+    check_topk(s2, r2, c2, full, None, 10, tol=TOL)  # same rows except near-ties inside the tolerance
+    assert np.array_equal(c1, c2)
     idx.close()
 
 
@@ -210,4 +219,67 @@ def test_large_batch_and_large_corpus_properties(native):
     assert (s[:, 1] < 0.5).all()                       # random 384-d vectors are nearly orthogonal
     s1, r1, c1 = idx.query(q[:4], k, path=native.PATH_SCAN)
     assert np.array_equal(r1[:, 0], planted[:4]) and np.abs(s1 - s[:4]).max() <= TOL
+    idx.close()
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("D", [8, 64, 100, 128])
+def test_short_rows_meet_the_tolerance_through_the_query_split(native, D, variant):
+    """Sparse / short vectors are the worst case of a bf16 query (error up to 2^-9 * sum|q_i c_i|): the split keeps
+    K3 within 2e-5 of the fp32 oracle -- far inside the north star's 1e-3 -- at every dimension AUTO routes to it."""
+    rng = np.random.default_rng(D)
+    n, B, k = 30000, 40, 10
+    x = rng.standard_normal((n, D)).astype(np.float32)
+    x[:, 3:] *= (rng.random((n, D - 3)) < 0.1)          # mostly-zero rows: a handful of non-zeros each
+    q = rng.standard_normal((B, D)).astype(np.float32)
+    q[:, 3:] *= (rng.random((B, D - 3)) < 0.2)
+    idx = native.NativeIndex(D)
+    idx.upsert(x)
+    stored, scale, _, _ = idx.get_rows(np.arange(n))
+    full = oracle_full_scores(stored, scale, q)
+    got = idx.debug_mma_scores(q, path=variant_path(native, variant))
+    assert np.abs(got - full).max() <= 2e-5, np.abs(got - full).max()
+    s, r, c = idx.query(q, k, path=variant_path(native, variant))
+    check_topk(s, r, c, full, None, k, tol=2e-5)
+    s, r, c = idx.query(q, k)  # AUTO
+    check_topk(s, r, c, full, None, k, tol=2e-5 if idx.stats().last_path == native.PATH_MMA else 2e-6)
+    # the plain bf16 tile, for contrast, is only good to its analytic bound
+    one = idx.debug_mma_scores(q, path=variant_path(native, variant), precision=native.PRECISION_BF16)
+    assert np.abs(one - bf16_query_scores(stored, scale, q, split=False)).max() <= 3e-6
+    idx.close()
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_forced_split_at_384(native, variant):
+    idx, stored, scale, rng = build(native, 50000, 384, seed=77)
+    q = rng.standard_normal((70, 384)).astype(np.float32)
+    full = oracle_full_scores(stored, scale, q)
+    got = idx.debug_mma_scores(q, path=variant_path(native, variant), precision=native.PRECISION_SPLIT)
+    assert np.abs(got - full).max() <= 1e-5
+    s, r, c = idx.query(q, 10, path=variant_path(native, variant), precision=native.PRECISION_SPLIT)
+    check_topk(s, r, c, full, None, 10, tol=1e-5)
+    with pytest.raises(Exception):
+        idx2 = native.NativeIndex(768)
+        idx2.upsert(rng.standard_normal((100, 768)).astype(np.float32))
+        idx2.query(q[:, :1].repeat(768, axis=1), 5, path=native.PATH_MMA, precision=native.PRECISION_SPLIT)
+    idx.close()
+
+
+def test_back_to_back_batches_share_self_resetting_state(native):
+    """The fused tail leaves the cross-CTA thresholds / counters zero for the next launch: batches of changing size,
+    k, path and predicate on ONE index (one query context) must each be exact."""
+    rng = np.random.default_rng(5)
+    n, D = 120_000, 384
+    ns = rng.integers(1, 4, n).astype(np.uint32)
+    idx, stored, scale, rng = build(native, n, D, seed=6, ns_codes=ns)
+    plan = [(200, 10, native.PATH_MMA, None), (5, 50, native.PATH_MMA_1CTA, None), (300, 10, native.PATH_MMA_2CTA, 2),
+            (1, 10, native.PATH_MMA, None), (129, 64, native.PATH_MMA, None), (16, 100, native.PATH_MMA, None),
+            (64, 10, native.PATH_MMA, 3), (1024, 10, native.PATH_MMA, None), (3, 1, native.PATH_MMA_2CTA, None),
+            (200, 10, native.PATH_MMA, None)]
+    for rep in range(2):
+        for B, k, path, code in plan:
+            q = rng.standard_normal((B, D)).astype(np.float32)
+            kw = {} if code is None else {"ns_code": code}
+            s, r, c = idx.query(q, k, path=path, **kw)
+            check_topk(s, r, c, bf16_query_scores(stored, scale, q), None if code is None else ns == code, k, tol=3e-6)
     idx.close()

@@ -167,7 +167,9 @@ def test_scan_predicates(native):
     assert (c == 0).all() and (r == -1).all()
     # oracle's own predicate path agrees
     es, er, ec = bf.query(stored, scale, q, k, mask_words=words, ns=ns, ns_code=5)
-    assert np.array_equal(ec, c) or True
+    assert np.array_equal(ec, c) and np.abs(es - s).max() <= 2e-6
+    for b in range(q.shape[0]):
+        assert set(er[b, :ec[b]].tolist()) == set(r[b, :c[b]].tolist()) or np.abs(es[b] - s[b]).max() <= 2e-6
     idx.close()
 
 
@@ -359,4 +361,21 @@ def test_stats_and_profiling(native):
     assert st.rows == 10000 and st.queries == 1 and st.kernel_launches >= 3
     assert st.last_query_ms > 0 and st.last_path == native.PATH_SCAN
     assert st.last_query_bytes == 10000 * (2 * 384 + 4)
+    idx.close()
+
+
+@pytest.mark.parametrize("B", [1, 2, 4])
+def test_scan_k_sequence_on_one_index(native, B):
+    """One long-lived index, n_results 100 -> 10 -> 100 -> 128 -> 1: the scan kernels' dynamic shared-memory limit is
+    a per-function attribute that must never be lowered under a cached launch plan."""
+    rng = np.random.default_rng(B)
+    n, D = 50000, 384
+    x = rng.standard_normal((n, D)).astype(np.float32)
+    idx = make_index(native, x)
+    stored, scale, _, _ = stored_of(idx)
+    q = rng.standard_normal((B, D)).astype(np.float32)
+    full = oracle_full_scores(stored, scale, q)
+    for k in (100, 10, 100, 128, 1, 50, 100):
+        s, r, c = idx.query(q, k, path=native.PATH_SCAN)
+        check_topk(s, r, c, full, None, k, tol=2e-6)
     idx.close()
