@@ -54,6 +54,8 @@ def parse_args():
                     help="multi-GPU top-k exchange: fused NVLink peer stores inside the kernels, or NCCL all-gather + K4")
     ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline and the configs sweep")
     ap.add_argument("--cpu-sample-rows", type=int, default=2_000_000)
+    ap.add_argument("--batch-leg", type=int, default=1024, help="batch size of the second (tensor-path) leg on the same corpus")
+    ap.add_argument("--no-batch-leg", action="store_true", help="headline leg only")
     return ap.parse_args()
 
 
@@ -66,18 +68,35 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def kernel_source_hash() -> str:
+    """sha256 over the CUDA sources of the query kernels: stamps an ncu capture with the code it measured."""
+    import hashlib
+
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, "codd_query_engine_b200", "csrc")
+    for name in ("common.cuh", "k2_scan.cuh", "k3_mma.cu"):
+        with open(os.path.join(csrc, name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
 def traffic_for(kernel: str, rows: int, dim: int, batch: int):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed
-    `ncu --set full` capture (profiles/traffic.json).  The capture is per launch at the captured row
-    count; DRAM traffic of a streaming scan is linear in rows, so it is scaled by rows/captured_rows
-    when the row count differs (same dim and batch only), else None."""
+    `ncu --set full` capture (profiles/traffic.json) -- reported ONLY when that capture was taken from the kernel
+    sources this run executes (traffic.json carries their hash); a stale capture yields None, never a number.
+    DRAM traffic of a streaming scan is linear in rows, so a capture at another row count (same dim and batch) is
+    scaled by rows/captured_rows.  Returns (bytes or None, note)."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     if not os.path.exists(path):
-        return None
-    t = json.load(open(path)).get(kernel)
+        return None, "no ncu capture committed"
+    doc = json.load(open(path))
+    t = doc.get(kernel)
     if not t or t.get("dim") != dim or t.get("batch") != batch:
-        return None
-    return float(t["bytes_per_launch"]) * (rows / float(t["rows"]))
+        return None, "no ncu capture of this kernel at this dim / batch"
+    have = kernel_source_hash()
+    if t.get("kernel_source_hash") != have:
+        return None, f"ncu capture is of kernel sources {t.get('kernel_source_hash')}, this run executes {have}: not reported"
+    return float(t["bytes_per_launch"]) * (rows / float(t["rows"])), f"{t.get('source')} (kernel sources {have}), scaled by rows"
 
 
 # --------------------------------------------------------------------------------------------- clocks
@@ -150,6 +169,15 @@ def load_c_oracle():
     return lib
 
 
+def host_threads() -> int:
+    """Every core this process may run on.  torch.distributed.run exports OMP_NUM_THREADS=1 to its workers; the
+    CPU arm is supposed to use the whole host, so the count is passed to the oracle explicitly."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_time_queries(lib, stored, scale, q, k, reps):
     """Seconds per query batch of the OpenMP oracle over `stored` (all host threads)."""
     n, D = stored.shape
@@ -163,7 +191,7 @@ def cpu_time_queries(lib, stored, scale, q, k, reps):
         t0 = time.perf_counter()
         threads = lib.cvo_query(P(stored), P(scale), ctypes.c_int64(n), ctypes.c_int32(D), P(qhat), ctypes.c_int32(B),
                                 ctypes.c_int32(k), None, None, ctypes.c_uint32(0xFFFFFFFF), None,
-                                ctypes.c_uint32(0xFFFFFFFF), ctypes.c_int64(0), P(out), ctypes.c_int32(0))
+                                ctypes.c_uint32(0xFFFFFFFF), ctypes.c_int64(0), P(out), ctypes.c_int32(host_threads()))
         times.append(time.perf_counter() - t0)
     return times, int(threads), out
 
@@ -184,6 +212,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    os.environ.pop("OMP_NUM_THREADS", None)  # (the launcher's per-worker default of 1 is not meant for this arm)
     lib = load_c_oracle()
     sample = min(args.cpu_sample_rows, args.rows)
     stored, scale = make_cpu_sample(lib, sample, args.dim)
@@ -191,13 +220,17 @@ def run_reference(args):
     cpu_time_queries(lib, stored, scale, q, args.k, max(args.warmup, 1))
     times, threads, _ = cpu_time_queries(lib, stored, scale, q, args.k, args.steps)
     per_step_sample = float(np.sum(times)) / args.steps
-    per_step_full = per_step_sample * (args.rows / sample)
+    scale_factor = args.rows / sample
+    per_step_full = per_step_sample * scale_factor
     qps = args.batch / per_step_full
-    sample_txt = (f"each step scans a {sample}-row sample of the {args.rows}-row corpus with the OpenMP C oracle "
-                  f"(oracle/brute_force.c, exact fp32-accumulate scan over the same bf16 rows); time scaled by rows/sample")
+    sample_txt = (f"each step scans a {sample}-row sample of the {args.rows}-row corpus with the OpenMP C oracle on {threads} "
+                  f"threads (oracle/brute_force.c, exact fp32-accumulate scan over the same bf16 rows); ms_per_step is the "
+                  f"MEASURED time of one sample step, value = batch / (ms_per_step x sample_scale), sample_scale = rows/sample "
+                  f"= {scale_factor:.1f} (a linear scan: time is proportional to rows)")
     line = {
         "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": per_step_full * 1e3, "higher_is_better": True, "scaling": "strong",
+        "warmup": args.warmup, "ms_per_step": per_step_sample * 1e3, "sample_scale": scale_factor,
+        "ms_per_step_full_workload": per_step_full * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": dict(workload_config(args), arithmetic="bf16 rows x fp32 query, fp32 accumulate (CPU oracle port)"),
         "cpu_baseline": {"value": qps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample_txt},
@@ -252,6 +285,146 @@ def time_steps(torch, dist, world, fn, steps, warmup):
     return float(ms.item()) * 1e-3
 
 
+def planted_queries(torch, device, D, total_rows, B):
+    """B queries that ARE corpus rows (the raw fp32 vectors the rows were built from), spread over up to 8 chunks
+    of the corpus and always including its LAST row (which lives in the last shard).  The corpus is generated
+    chunk by chunk from seeded Philox streams, so every rank can regenerate any chunk.  Returns (q [B][D] on the
+    device, global rows int64 [B])."""
+    n_chunks = -(-total_rows // CHUNK_ROWS)
+    nc = max(1, min(8, n_chunks, B))
+    chunks = sorted({n_chunks - 1} | {int(round(i * (n_chunks - 1) / max(nc - 1, 1))) for i in range(nc)})
+    per = -(-B // len(chunks))
+    gen = torch.Generator(device=device)
+    qs, rows = [], []
+    for c in reversed(chunks):  # last chunk first: query 0 is the corpus's last row
+        gen.manual_seed(1000 + c)
+        x = torch.randn((CHUNK_ROWS, D), device=device, generator=gen, dtype=torch.float32)
+        valid = min(CHUNK_ROWS, total_rows - c * CHUNK_ROWS)
+        local = valid - 1 - np.arange(min(per, valid), dtype=np.int64) * max(1, valid // per)  # distinct, last row first
+        qs.append(x[torch.from_numpy(local).to(device)].clone())
+        rows.append(local + c * CHUNK_ROWS)
+        del x
+    q = torch.cat(qs)[:B].contiguous()
+    return q, np.concatenate(rows)[:B]
+
+
+def parity_probe(torch, index, planted_q, planted_rows, k, path, world):
+    """Planted-row probe of one leg: every query is a stored row, so its top hit must be that row with cosine ~ 1,
+    results must be ordered, distinct and complete.  Goes through the same sharded search the leg times."""
+    from codd_query_engine_b200 import native
+
+    keys = index.query_device(planted_q, k, path=path)
+    torch.cuda.synchronize()
+    arr = keys.cpu().numpy().view(np.uint64)
+    scores, rows = native.decode_keys(arr)
+    problems = []
+    if not np.array_equal(rows[:, 0], planted_rows):
+        bad = int((rows[:, 0] != planted_rows).sum())
+        problems.append(f"{bad} of {len(planted_rows)} planted rows are not the top hit")
+    if not (np.abs(scores[:, 0] - 1.0) < 2e-3).all():
+        problems.append(f"top scores deviate from 1 by up to {float(np.abs(scores[:, 0] - 1.0).max()):.2e}")
+    if not (arr[:, :-1] > arr[:, 1:]).all():
+        problems.append("keys are not strictly descending (score desc, row asc)")
+    if (arr == 0).any():
+        problems.append("fewer than k results")
+    return "ok" if not problems else "FAILED: " + "; ".join(problems)
+
+
+def run_leg(torch, dist, world, index, native, args, pk, B, k, D, path, steps, warmup, device, local_rows):
+    """One bench leg (a batch size): device-resident whole-job throughput, the dominant kernel alone with its
+    roofline, and the end-to-end number through the host API."""
+    gq = torch.Generator(device=device).manual_seed(1 + B)
+    q_dev = torch.randn((B, D), device=device, generator=gq, dtype=torch.float32)
+    q_host = q_dev.cpu().numpy()
+
+    secs = time_steps(torch, dist, world, lambda: index.query_device(q_dev, k, path=path), steps, warmup)
+    l0 = index.local.stats().kernel_launches
+    index.query_device(q_dev, k, path=path)
+    per_step_launches = index.local.stats().kernel_launches - l0 + (1 if world > 1 and index.exchange == "nccl" else 0)  # + K4
+    ms_per_step = secs / steps * 1e3
+    value = B * steps / secs
+
+    # ---- dominant kernel alone (per-GPU scan of the local shard), CUDA events on the launch stream
+    local_keys = torch.zeros((B, k), dtype=torch.int64, device=device)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def scan_only():
+        index.local.query_device(q_dev.data_ptr(), B, k, local_keys.data_ptr(), path=path, stream=stream)
+
+    ksecs = time_steps(torch, dist, world, scan_only, steps, max(warmup, 3))
+    st = index.local.stats()
+    kernel_ms = ksecs / steps * 1e3
+    used_path = st.last_path
+    dp = st.dim_padded
+    long_step = kernel_ms >= 20.0  # a kernel that runs for tens of ms sees the sustained clocks, not the burst ones
+    if used_path == native.PATH_MMA:
+        flops = 2.0 * B * local_rows * dp
+        tf = flops / (kernel_ms * 1e-3) / 1e12
+        bytes_alg = local_rows * (2 * dp + 4)
+        gbs = bytes_alg / (kernel_ms * 1e-3) / 1e9
+        tpeak = pk["bf16_tflops_sustained"] if long_step else pk["bf16_tflops"]
+        hbm_frac, tensor_frac = gbs / pk["hbm_gbs"], tf / tpeak
+        if tensor_frac >= hbm_frac:
+            roof = {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tensor_frac,
+                    "algorithmic_flops_per_launch": flops}
+        else:
+            roof = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hbm_frac}
+        kernel_name = "k_mma_topk"
+    else:
+        passes = -(-B // 4) if dp <= 384 else (-(-B // 2) if dp <= 768 else B)
+        bytes_alg = local_rows * (2 * dp + 4) * passes
+        gbs = bytes_alg / (kernel_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"]}
+        kernel_name = "k_scan_topk"
+    traffic, traffic_note = traffic_for(kernel_name, local_rows, D, B)
+    roof.update({"traffic": traffic, "traffic_source": traffic_note, "kernel": kernel_name, "kernel_ms": kernel_ms,
+                 "algorithmic_bytes_per_launch": bytes_alg,
+                 "peak_source": pk["source"] + (" (sustained; the kernel runs for tens of ms)" if long_step and used_path == native.PATH_MMA
+                                                else " (burst; kernel timed alone)")})
+
+    # ---- end to end through the host API (pinned H2D of the batch + D2H of the result every step)
+    def e2e_step():
+        index.query(q_host, k, path=path)
+
+    for _ in range(max(warmup, 3)):
+        e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_secs = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_secs, op=dist.ReduceOp.MAX)
+    e2e_value = B * steps / float(e2e_secs.item())
+
+    # ---- correctness signal of this leg, at this N: planted rows through the same sharded search
+    pq, prow = planted_queries(torch, device, D, args.rows, B)
+    parity = parity_probe(torch, index, pq, prow, k, path, world)
+    del pq
+
+    leg = {
+        "value": value, "unit": UNIT, "ms_per_step": ms_per_step, "steps": steps, "warmup": warmup, "batch": B, "k": k,
+        "arithmetic": ("bf16 rows x fp32 query, fp32 accumulate (K2 scan)" if used_path != native.PATH_MMA
+                       else "bf16 rows x bf16 queries on tcgen05, fp32 accumulate in TMEM (K3)"),
+        "roofline": roof,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": B * k * 8,
+                "api": ("ShardedIndex.query -> cv_query (C-ABI, host buffers in and out)" if world == 1 else
+                        "ShardedIndex.query -> cv_query_exchange (C-ABI, host buffers in and out, fused NVLink exchange)"
+                        if index.exchange == "fused" else "ShardedIndex.query -> cv_query_device + NCCL all-gather + K4, pinned host buffers")},
+        "gpu_launches": int(per_step_launches * steps), "launches_per_step": int(per_step_launches),
+        "parity_check": parity,
+    }
+    if world > 1 and index.exchange == "fused":
+        # BASELINE.json configs[3] as literally written: per-GPU top-k + NCCL all-gather + merge kernel
+        nsecs = time_steps(torch, dist, world, lambda: index.query_device(q_dev, k, path=path, exchange="nccl"),
+                           steps, max(warmup, 3))
+        leg["nccl_allgather_merge"] = {"value": B * steps / nsecs, "unit": UNIT, "ms_per_step": nsecs / steps * 1e3}
+    return leg, q_host
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -274,105 +447,59 @@ def run_ours(args):
     path = {"auto": native.PATH_AUTO, "scan": native.PATH_SCAN, "mma": native.PATH_MMA}[args.path]
     B, k, D = args.batch, args.k, args.dim
     pk = peaks()
+    big = 0 if args.no_batch_leg or B >= args.batch_leg else args.batch_leg
 
     t_build = time.perf_counter()
-    index = ShardedIndex(D, args.rows, device=device, exchange=args.exchange, max_queries=max(B, 1), max_k=max(k, 1))
+    index = ShardedIndex(D, args.rows, device=device, exchange=args.exchange, max_queries=max(B, big, 1), max_k=max(k, 1))
     build_shard(index, index.lo, index.hi, D, torch, device)
     torch.cuda.synchronize()
     local_rows = len(index.local)
     t_build = time.perf_counter() - t_build
 
-    gq = torch.Generator(device=device).manual_seed(1)
-    q_dev = torch.randn((B, D), device=device, generator=gq, dtype=torch.float32)
-    q_host = q_dev.cpu().numpy()
-
-    # ---- device-resident throughput: the whole job (scan + all-gather + merge), max over ranks
     with ClockSampler(local_rank) as clk:
-        secs = time_steps(torch, dist, world, lambda: index.query_device(q_dev, k, path=path), args.steps, args.warmup)
-    l0 = index.local.stats().kernel_launches
-    index.query_device(q_dev, k, path=path)
-    per_step_launches = index.local.stats().kernel_launches - l0 + (1 if world > 1 and index.exchange == "nccl" else 0)  # + K4
-    launches = int(per_step_launches * args.steps)
-    ms_per_step = secs / args.steps * 1e3
-    value = B * args.steps / secs
-
-    # ---- dominant kernel alone (per-GPU scan of the local shard), CUDA events on the launch stream
-    local_keys = torch.zeros((B, k), dtype=torch.int64, device=device)
-    stream = torch.cuda.current_stream().cuda_stream
-
-    def scan_only():
-        index.local.query_device(q_dev.data_ptr(), B, k, local_keys.data_ptr(), path=path, stream=stream)
-
-    ksecs = time_steps(torch, dist, world, scan_only, args.steps, max(args.warmup, 3))
-    st = index.local.stats()
-    kernel_ms = ksecs / args.steps * 1e3
-    used_path = st.last_path
-    dp = st.dim_padded
-    if used_path == native.PATH_MMA:
-        flops = 2.0 * B * local_rows * dp
-        tf = flops / (kernel_ms * 1e-3) / 1e12
-        bytes_alg = local_rows * (2 * dp + 4)
-        gbs = bytes_alg / (kernel_ms * 1e-3) / 1e9
-        hbm_frac, tensor_frac = gbs / pk["hbm_gbs"], tf / pk["bf16_tflops"]
-        if tensor_frac >= hbm_frac:
-            roof = {"bound": "tensor", "achieved": tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": tensor_frac}
-        else:
-            roof = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hbm_frac}
-        kernel_name = "k_mma_topk"
-    else:
-        passes = -(-B // 4) if dp <= 384 else (-(-B // 2) if dp <= 768 else B)
-        bytes_alg = local_rows * (2 * dp + 4) * passes
-        gbs = bytes_alg / (kernel_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"]}
-        kernel_name = "k_scan_topk"
-    roof.update({"traffic": traffic_for(kernel_name, local_rows, D, B), "kernel": kernel_name, "kernel_ms": kernel_ms,
-                 "algorithmic_bytes_per_launch": bytes_alg, "peak_source": pk["source"] + " (burst; kernel timed alone)"})
-
-    # ---- end to end through the host API (pinned H2D of the batch + D2H of the result every step)
-    def e2e_step():
-        index.query(q_host, k, path=path)
-
-    for _ in range(max(args.warmup, 3)):
-        e2e_step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    e2e_secs = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_secs, op=dist.ReduceOp.MAX)
-    e2e_value = B * args.steps / float(e2e_secs.item())
+        head, q_host = run_leg(torch, dist, world, index, native, args, pk, B, k, D, path, args.steps, args.warmup, device,
+                               local_rows)
+    legs = {}
+    if big:
+        # the tensor-path leg on the SAME corpus at the same N (BASELINE.json configs[3]: batch 1024)
+        with ClockSampler(local_rank) as clk_big:
+            leg, _ = run_leg(torch, dist, world, index, native, args, pk, big, k, D, native.PATH_AUTO, max(3, min(args.steps, 10)),
+                             max(3, min(args.warmup, 5)), device, local_rows)
+        leg["clocks"] = clk_big.summary()
+        legs[f"batch{big}"] = leg
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "bf16",
         "data": "synthetic",
-        "config": dict(workload_config(args), arithmetic="bf16 rows x fp32 query, fp32 accumulate (K2 scan)"
-                       if used_path != native.PATH_MMA else "bf16 rows x bf16 queries on tcgen05, fp32 accumulate in TMEM (K3)"),
-        "roofline": roof,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": B * k * 8,
-                "api": ("ShardedIndex.query -> cv_query (C-ABI, host buffers in and out; the query rides in the kernel "
-                        "parameters, the keys land in page-locked host memory)" if world == 1 else
-                        "ShardedIndex.query -> cv_query_device_exchange (C-ABI) with pinned host buffers")},
-        "gpu_launches": launches,
+        "config": dict(workload_config(args), arithmetic=head["arithmetic"]),
+        "roofline": head["roofline"],
+        "e2e": head["e2e"],
+        "gpu_launches": head["gpu_launches"] + sum(l["gpu_launches"] for l in legs.values()),
+        "parity_check": head["parity_check"],
         "clocks": clk.summary(),
+        "legs": legs,
         "build_seconds": t_build, "rows_per_gpu": local_rows,
         "exchange": index.exchange if world > 1 else "none (1 GPU)",
+        "kernel_source_hash": kernel_source_hash(),
     }
 
     if rank == 0 and world == 1 and not args.no_extras:
         line["cpu_baseline"] = cpu_baseline(args, index, q_host)
+        index.close()  # free the corpus before the small-config sweep builds its own
         line["configs"] = sweep_small_configs(torch, native, D, k, pk)
         line["reference_case"] = reference_case(torch, native, D, k)
+    else:
+        index.close()
     if rank == 0:
         print(json.dumps(line))
-    index.close()
     if world > 1:
         dist.destroy_process_group()
+    failed = [name for name, chk in [("headline", head["parity_check"])] + [(n, l["parity_check"]) for n, l in legs.items()]
+              if chk != "ok"]
+    if failed:
+        raise SystemExit(f"bench.py: parity probe failed in {failed}")
 
 
 def cpu_baseline(args, index, q_host):
@@ -407,7 +534,7 @@ def sweep_small_configs(torch, native, D, k, pk):
         idx.upsert_device(x.data_ptr(), rows)
         del x
         stream = torch.cuda.current_stream().cuda_stream
-        for B in (1, 4, 16, 64, 256, 1024):
+        for B in (1, 2, 4, 16, 64, 256, 1024):
             q = torch.randn((B, D), device="cuda", generator=gen)
             keys = torch.zeros((B, k), dtype=torch.int64, device="cuda")
             fn = lambda: idx.query_device(q.data_ptr(), B, k, keys.data_ptr(), stream=stream)  # noqa: E731
@@ -423,11 +550,16 @@ def sweep_small_configs(torch, native, D, k, pk):
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / iters
             st = idx.stats()
+            bytes_alg = rows * (2 * st.dim_padded + 4)
+            flops = 2.0 * B * rows * st.dim_padded
+            ideal_ms = max(bytes_alg / pk["hbm_gbs"] / 1e6, flops / pk["bf16_tflops_sustained"] / 1e9)
             out.append({"workload": f"1M x {D} bf16, batch {B}, top-{k}", "ms_per_batch": ms, "qps": B / ms * 1e3,
                         "path": "mma" if st.last_path == native.PATH_MMA else "scan",
-                        "scan_gbs_single_pass": rows * (2 * st.dim_padded + 4) / ms / 1e6,
-                        "tflops": 2.0 * B * rows * st.dim_padded / ms / 1e9,
-                        "hbm_frac_single_pass": rows * (2 * st.dim_padded + 4) / ms / 1e6 / pk["hbm_gbs"]})
+                        "scan_gbs_single_pass": bytes_alg / ms / 1e6, "tflops": flops / ms / 1e9,
+                        "hbm_frac_single_pass": bytes_alg / ms / 1e6 / pk["hbm_gbs"],
+                        "ideal_ms": ideal_ms, "frac_of_roofline": ideal_ms / ms,
+                        "roofline_note": "ideal = max(one pass of the algorithmic bytes at the measured HBM peak, flops at the "
+                                         "sustained bf16 peak); the whole batch incl. every launch it needs"})
         idx.close()
     except Exception as exc:
         out.append({"error": str(exc)})

@@ -35,8 +35,8 @@ import numpy as np
 
 from . import native
 from .embedding import default_embedding_function
-from .native import NativeIndex
-from .where import compile_where, evaluate, validate_where
+from .native import NativeIndex, StripedIndex
+from .where import MetadataColumns, compile_where, validate_where
 
 DEFAULT_LABEL_FIELD = "category"
 _QUERY_INCLUDE = ("metadatas", "documents", "distances")
@@ -63,6 +63,21 @@ def _space_to_metric(metadata: Optional[dict]) -> int:
     raise ValueError(f"hnsw:space={space!r} is not supported (cosine and ip only)")
 
 
+def _device_list(metadata: Optional[dict], device: int) -> list[int]:
+    """Devices a collection lives on: `coddvec:devices` in the collection metadata, else CODDVEC_DEVICES in the
+    environment ("0,1,2,3", or "all") -- the zero-edit switch that lets the reference's single-process service
+    (codd_lib/codd_lib/client/provider/promql_module.py:59-67) stripe its collection over several GPUs -- else the
+    one device of `coddvec:device` / CODDVEC_DEVICE."""
+    spec = (metadata or {}).get("coddvec:devices") or os.environ.get("CODDVEC_DEVICES")
+    if spec is None or str(spec).strip() == "":
+        return [int((metadata or {}).get("coddvec:device", device))]
+    if isinstance(spec, (list, tuple)):
+        return [int(d) for d in spec]
+    if str(spec).strip().lower() == "all":
+        return list(range(max(1, native.device_count())))
+    return [int(d) for d in str(spec).replace(";", ",").split(",") if d.strip() != ""]
+
+
 def _as_list(x) -> list:
     if x is None:
         return []
@@ -82,11 +97,14 @@ class Collection:
         self.metadata = dict(metadata) if metadata else None
         self._metric = _space_to_metric(metadata)
         self._embed = embedding_function or default_embedding_function()
-        self._device = int((metadata or {}).get("coddvec:device", device))
+        self._devices = _device_list(metadata, device)
+        self._device = self._devices[0]
         self._label_field = str((metadata or {}).get("coddvec:label_field", DEFAULT_LABEL_FIELD))
         self._capacity_rows = int((metadata or {}).get("coddvec:capacity_rows", capacity_rows))
         self._max_rows = int((metadata or {}).get("coddvec:max_rows", max_rows))
         self._lock = threading.RLock()
+        self._idle = threading.Condition(self._lock)
+        self._inflight = 0  # searches running on the device outside the lock (close() waits for them)
         self._index: Optional[NativeIndex] = None  # created on first upsert (dimension inferred, like chromadb)
         self._row_of: dict[str, int] = {}
         self._ids: list[Optional[str]] = []
@@ -97,12 +115,19 @@ class Collection:
         self._ns_codes: dict[Any, int] = {}
         self._label_codes: dict[Any, int] = {}
         self._ns_rows: dict[int, int] = {}  # live rows per namespace code (selectivity estimate for filtered batches)
+        self._columns = MetadataColumns()   # dictionary-encoded metadata fields `where` clauses have touched
+        self._generation = 0                # bumped by every write: keys the compiled-where cache
+        self._where_cache: dict[str, tuple[int, Any]] = {}
 
     # ------------------------------------------------------------------ helpers
     def _ensure_index(self, dim: int) -> NativeIndex:
         if self._index is None:
-            self._index = NativeIndex(dim, metric=self._metric, device=self._device,
-                                      capacity_rows=self._capacity_rows, max_rows=self._max_rows)
+            if len(self._devices) > 1:  # one process, several GPUs: rows striped over the devices (cv_group)
+                self._index = StripedIndex(dim, metric=self._metric, devices=self._devices,
+                                           capacity_rows=self._capacity_rows, max_rows=self._max_rows)
+            else:
+                self._index = NativeIndex(dim, metric=self._metric, device=self._device,
+                                          capacity_rows=self._capacity_rows, max_rows=self._max_rows)
         elif self._index.dim != dim:
             raise ValueError(f"Embedding dimension {dim} does not match collection dimensionality {self._index.dim}")
         return self._index
@@ -132,8 +157,8 @@ class Collection:
         if B < 2 or self._index is None:
             return native.PATH_AUTO
         live = max(len(self._row_of), 1)
-        if compiled.mask_words is not None:
-            eligible = int(np.unpackbits(compiled.mask_words.view(np.uint8)).sum())
+        if compiled.mask_bits is not None:
+            eligible = compiled.eligible
         elif compiled.ns_code != native.ANY:
             eligible = self._ns_rows.get(compiled.ns_code, 0)
         else:
@@ -214,10 +239,12 @@ class Collection:
             base = len(self._ids)
             rows = np.empty(n, dtype=np.int64)
             fresh = 0
+            reused = 0  # tombstoned slots taken from the END of _free_rows; popped only once the device has the batch
             for j, doc_id in enumerate(ids):
                 r = self._row_of.get(doc_id)
-                if r is None and self._free_rows:
-                    r = self._free_rows.pop()  # reuse a tombstoned row
+                if r is None and reused < len(self._free_rows):
+                    reused += 1
+                    r = self._free_rows[-reused]
                 if r is None:
                     r = -1
                     fresh += 1
@@ -225,7 +252,10 @@ class Collection:
             ns = np.fromiter((self._code(self._ns_codes, (m or {}).get("namespace")) for m in mds), dtype=np.uint32, count=n)
             lb = np.fromiter((self._code(self._label_codes, (m or {}).get(self._label_field)) for m in mds),
                              dtype=np.uint32, count=n)
-            got = index.upsert(emb, rows=rows, ns_codes=ns, label_codes=lb)
+            got = index.upsert(emb, rows=rows, ns_codes=ns, label_codes=lb)  # raises -> nothing below happens
+            if reused:
+                del self._free_rows[-reused:]
+            self._generation += 1
             if fresh:
                 grow = base + fresh - len(self._ids)
                 self._ids.extend([None] * grow)
@@ -242,6 +272,7 @@ class Collection:
                 self._metadatas[r] = mds[j]
                 self._documents[r] = None if documents is None else documents[j]
                 self._alive[r] = True
+                self._columns.set_row(r, mds[j])
 
     def upsert(self, ids, embeddings=None, metadatas=None, documents=None, **_ignored) -> None:
         """Insert-or-replace by id (vector, document and metadata are all replaced)."""
@@ -252,7 +283,8 @@ class Collection:
         self._write(ids, embeddings, metadatas, documents, replace=False)
 
     def update(self, ids, embeddings=None, metadatas=None, documents=None, **_ignored) -> None:
-        """Update existing ids only; unknown ids are ignored."""
+        """Update existing ids only; unknown ids are ignored.  Metadata is MERGED into what the row has (chromadb's
+        update semantics); a changed namespace / label field is written through to the device's predicate columns."""
         ids = _as_list(ids)
         with self._lock:
             known = [j for j, i in enumerate(ids) if i in self._row_of]
@@ -261,32 +293,64 @@ class Collection:
             pick = lambda seq: None if seq is None else [_as_list(seq)[j] for j in known]  # noqa: E731
             sub_ids = [ids[j] for j in known]
             docs, mds = pick(documents), pick(metadatas)
+            merged = None
+            if mds is not None:
+                merged = []
+                for j, doc_id in enumerate(sub_ids):
+                    m = dict(self._metadatas[self._row_of[doc_id]] or {})
+                    m.update(self._check_metadata(mds[j]) or {})
+                    merged.append(m)
             if embeddings is None and docs is None:
+                if merged is None:
+                    return
+                rows, ns, lb = [], [], []
                 for j, doc_id in enumerate(sub_ids):  # metadata-only update keeps the vector
                     r = self._row_of[doc_id]
-                    if mds is not None:
-                        merged = dict(self._metadatas[r] or {})
-                        merged.update(self._check_metadata(mds[j]) or {})
-                        self._metadatas[r] = merged
+                    old = self._metadatas[r] or {}
+                    new = merged[j]
+                    if old.get("namespace") != new.get("namespace") or old.get(self._label_field) != new.get(self._label_field):
+                        rows.append(r)
+                        ns.append(self._code(self._ns_codes, new.get("namespace")))
+                        lb.append(self._code(self._label_codes, new.get(self._label_field)))
+                if rows:  # the fused predicates read the device columns: rewrite them before the host tables change
+                    self._index.set_codes(np.asarray(rows, dtype=np.int64), np.asarray(ns, dtype=np.uint32),
+                                          np.asarray(lb, dtype=np.uint32))
+                for j, doc_id in enumerate(sub_ids):
+                    r = self._row_of[doc_id]
+                    self._ns_count(self._metadatas[r], -1)
+                    self._metadatas[r] = merged[j]
+                    self._ns_count(merged[j], +1)
+                    self._columns.set_row(r, merged[j])
+                self._generation += 1
                 return
             emb = None if embeddings is None else np.asarray(embeddings, dtype=np.float32)[known]
-            if mds is None:
-                mds = [self._metadatas[self._row_of[i]] for i in sub_ids]
+            if merged is None:
+                merged = [self._metadatas[self._row_of[i]] for i in sub_ids]
             if docs is None:
                 docs = [self._documents[self._row_of[i]] for i in sub_ids]
-            self._write(sub_ids, emb, mds, docs, replace=True)
+            if emb is None and any(d is None for d in docs):
+                raise ValueError("update needs embeddings for rows that have no document to embed")
+            self._write(sub_ids, emb, merged, docs, replace=True)
 
     def delete(self, ids=None, where=None, **_ignored) -> None:
-        """Tombstone rows; their slots are reused by later inserts and masked out of queries."""
+        """Tombstone rows: the device marks them dead (no query returns them, no per-query mask is needed) and their
+        slots are reused by later inserts."""
         with self._lock:
             if ids is None and where is None:
                 raise ValueError("delete needs ids or where")
-            targets = [self._row_of[i] for i in _as_list(ids) if i in self._row_of] if ids is not None else \
-                [r for r in range(len(self._ids)) if self._alive[r]]
+            if ids is not None:
+                targets = np.asarray([self._row_of[i] for i in _as_list(ids) if i in self._row_of], dtype=np.int64)
+            else:
+                targets = np.nonzero(self._alive)[0].astype(np.int64)
             if where is not None:
                 validate_where(where)
-                targets = [r for r in targets if evaluate(where, self._metadatas[r])]
-            for r in targets:
+                hit = self._columns.evaluate_rows(where, self._metadatas) & self._alive
+                targets = targets[hit[targets]]
+            if targets.size == 0:
+                return
+            self._index.delete_rows(np.sort(targets))  # raises -> host tables untouched
+            self._generation += 1
+            for r in targets.tolist():
                 self._ns_count(self._metadatas[r], -1)
                 self._row_of.pop(self._ids[r], None)
                 self._ids[r] = None
@@ -294,6 +358,7 @@ class Collection:
                 self._documents[r] = None
                 self._alive[r] = False
                 self._free_rows.append(r)
+                self._columns.set_row(r, None)
 
     # ------------------------------------------------------------------ reads
     def count(self) -> int:
@@ -325,10 +390,11 @@ class Collection:
             if ids is not None:
                 rows = [self._row_of[i] for i in _as_list(ids) if i in self._row_of]
             else:
-                rows = [r for r in range(len(self._ids)) if self._alive[r]]
+                rows = np.nonzero(self._alive)[0].tolist()
             if where is not None:
                 validate_where(where)
-                rows = [r for r in rows if evaluate(where, self._metadatas[r])]
+                hit = self._columns.evaluate_rows(where, self._metadatas)
+                rows = [r for r in rows if hit[r]]
             if offset:
                 rows = rows[int(offset):]
             if limit is not None:
@@ -398,31 +464,58 @@ class Collection:
                 return empty()
             if q.shape[1] != self._index.dim:
                 raise ValueError(f"Embedding dimension {q.shape[1]} does not match collection dimensionality {self._index.dim}")
-            compiled = compile_where(where, self._metadatas, self._ns_codes, self._label_field, self._label_codes,
-                                     alive=self._alive if self._free_rows else None)
+            compiled = self._compile(where)
             if compiled.empty:
                 return empty()
             k = min(int(n_results), native.MAX_K, len(self._row_of))
-            scores, rows, counts = self._index.query(q, k, ns_code=compiled.ns_code, label_code=compiled.label_code,
-                                                     mask=compiled.mask_words, path=self._filtered_batch_path(B, compiled))
-            if self._metric == native.METRIC_COSINE:
-                np.clip(scores, -1.0, 1.0, out=scores)
-            res = empty()
-            hits = rows.tolist()
-            counts = counts.tolist()
-            dist = (np.float32(1.0) - scores).tolist() if "distances" in include else None  # fp32 arithmetic, like Chroma
+            index, path = self._index, self._filtered_batch_path(B, compiled)
+            self._inflight += 1
+        # The search runs OUTSIDE the collection lock: the C-ABI serves concurrent queries (each on its own stream),
+        # appends never disturb a running scan, and deletes / overwrites are ordered against it on the device.
+        try:
+            kw = {"mask_bits": compiled.mask_bits} if compiled.mask_bits is not None else {}
+            scores, rows, counts = index.query(q, k, ns_code=compiled.ns_code, label_code=compiled.label_code, path=path, **kw)
+        finally:
+            with self._lock:
+                self._inflight -= 1
+                self._idle.notify_all()
+        if self._metric == native.METRIC_COSINE:
+            np.clip(scores, -1.0, 1.0, out=scores)
+        res = empty()
+        hits = rows.tolist()
+        counts = counts.tolist()
+        dist = (np.float32(1.0) - scores).tolist() if "distances" in include else None  # fp32 arithmetic, like Chroma
+        with self._lock:  # rows -> ids / metadata / documents (a row deleted since the scan is dropped)
             for b in range(B):
                 hit = hits[b][: counts[b]]
+                keep = [j for j, r in enumerate(hit) if r < len(self._ids) and self._ids[r] is not None]
+                hit = [hit[j] for j in keep]
                 res["ids"][b] = [self._ids[r] for r in hit]
                 if dist is not None:
-                    res["distances"][b] = dist[b][: len(hit)]
+                    res["distances"][b] = [dist[b][j] for j in keep]
                 if "metadatas" in include:
                     res["metadatas"][b] = [dict(self._metadatas[r]) if self._metadatas[r] is not None else None for r in hit]
                 if "documents" in include:
                     res["documents"][b] = [self._documents[r] for r in hit]
                 if "embeddings" in include:
                     res["embeddings"][b] = self._stored_vectors(hit)
-            return res
+        return res
+
+    def _compile(self, where):
+        """`where` -> fused codes + bitmask, cached per (clause, write generation): a service repeats the same handful
+        of filters between writes."""
+        if not where:
+            return compile_where(None, self._metadatas, self._ns_codes, self._label_field, self._label_codes)
+        key = json.dumps(where, sort_keys=True, default=str)
+        hit = self._where_cache.get(key)
+        if hit is not None and hit[0] == self._generation:
+            return hit[1]
+        compiled = compile_where(where, self._metadatas, self._ns_codes, self._label_field, self._label_codes,
+                                 columns=self._columns)
+        if len(self._where_cache) >= 64:
+            self._where_cache.clear()
+        self._where_cache[key] = (self._generation, compiled)
+        return compiled
 
     def modify(self, name: Optional[str] = None, metadata: Optional[dict] = None) -> None:
         if name is not None:
@@ -501,6 +594,8 @@ class Collection:
         if batcher is not None:
             batcher.close()  # outside the lock: its worker takes it to search
         with self._lock:
+            while self._inflight:
+                self._idle.wait()
             if self._index is not None:
                 self._index.close()
                 self._index = None

@@ -165,6 +165,7 @@ struct cv_index {
     int64_t last_bytes = 0;
     int32_t last_path = 0;
     std::atomic<int32_t> profiling{0};
+    std::atomic<bool> scale_bounded{true};  // every stored scale is 0, NaN or within 2^-7 of 1 (K3's raw-dot prefilter)
 
     ~cv_index() {
         ctx_free.clear();
@@ -360,6 +361,7 @@ int enqueue_query(cv_index* idx, QueryCtx* c, cudaStream_t stream, const float* 
         m.row_offset = static_cast<uint32_t>(idx->cfg.row_offset);
         m.row_stride = static_cast<uint32_t>(idx->row_stride);
         m.precision = p->precision;
+        m.scale_bounded = idx->scale_bounded.load();
         m.q = d_q;
         m.B = B;
         m.k = k;
@@ -550,7 +552,7 @@ int cv_create(const cv_config* cfg, cv_index** out) {
         !(err = idx->label.reserve(cfg->device, static_cast<size_t>(idx->max_rows) * 4)).empty())
         return fail(CV_ERR_CUDA, "%s", err.c_str());
     CV_CUDA(cudaStreamCreateWithFlags(&idx->upsert_stream, cudaStreamNonBlocking));
-    CV_CUDA(cudaMalloc(&idx->d_flag, sizeof(unsigned int)));
+    CV_CUDA(cudaMalloc(&idx->d_flag, 2 * sizeof(unsigned int)));  // [0] non-finite inputs, [1] a scale outside K3's bound
     if (cfg->capacity_rows > 0) {
         int rc = ensure_capacity(idx.get(), cfg->capacity_rows);
         if (rc) return rc;
@@ -564,6 +566,12 @@ void cv_destroy(cv_index* idx) {
     DeviceGuard dg(idx->cfg.device);
     (void)cudaDeviceSynchronize();
     delete idx;
+}
+
+int32_t cv_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    return n;
 }
 
 int64_t cv_count(const cv_index* idx) { return idx ? idx->n_committed.load(std::memory_order_acquire) : 0; }
@@ -610,8 +618,8 @@ static int upsert_impl(cv_index* idx, const int64_t* rows, const float* emb, con
     }
     if (overwrite && !on_device) {
         // overwrites destroy live rows: reject non-finite input before touching anything
-        for (int64_t i = 0; i < n; ++i) {
-            if (rows[i] < 0) continue;
+        for (int64_t i = 0; i < n; ++i) {  // every row of the batch, appended ones too: a failure after K1 has rewritten
+                                           // live rows could not be undone
             const float* r = emb + i * idx->D;
             for (int d = 0; d < idx->D; ++d) {
                 uint32_t u;
@@ -640,7 +648,19 @@ static int upsert_impl(cv_index* idx, const int64_t* rows, const float* emb, con
         if (label_codes && (rc = idx->stage_label.reserve(chunk_rows))) return rc;
     }
     if ((rc = idx->stage_rows.reserve(chunk_rows))) return rc;
-    CV_CUDA(cudaMemsetAsync(idx->d_flag, 0, sizeof(unsigned int), s));
+    CV_CUDA(cudaMemsetAsync(idx->d_flag, 0, 2 * sizeof(unsigned int), s));
+    if (overwrite && on_device) {
+        // device input cannot be pre-checked on the host: count non-finite values over the WHOLE input before the
+        // first K1 launch touches a live row
+        const int64_t total = n * idx->D;
+        int cgrid = static_cast<int>(std::min<int64_t>((total + 255) / 256, idx->sm_count * 8));
+        k_count_nonfinite<<<cgrid, 256, 0, s>>>(emb, total, idx->d_flag);
+        CV_CUDA(cudaGetLastError());
+        unsigned int bad = 0;
+        CV_CUDA(cudaMemcpyAsync(&bad, idx->d_flag, sizeof(bad), cudaMemcpyDeviceToHost, s));
+        CV_CUDA(cudaStreamSynchronize(s));
+        if (bad) return fail(CV_ERR_NONFINITE, "embeddings contain %u NaN/Inf values; nothing was written", bad);
+    }
 
     for (int64_t lo = 0; lo < n; lo += chunk_rows) {
         const int64_t m = std::min(chunk_rows, n - lo);
@@ -668,26 +688,22 @@ static int upsert_impl(cv_index* idx, const int64_t* rows, const float* emb, con
         a.scale = idx->scale.ptr<float>();
         a.ns = idx->ns.ptr<uint32_t>();
         a.label = idx->label.ptr<uint32_t>();
+        a.flags = idx->d_flag;
         const int64_t total = m * idx->D;
         int cgrid = static_cast<int>(std::min<int64_t>((total + 255) / 256, idx->sm_count * 8));
         k_count_nonfinite<<<cgrid, 256, 0, s>>>(a.x, total, idx->d_flag);
         CV_CUDA(cudaGetLastError());
-        if (overwrite && on_device) {
-            // cannot pre-check on the host: stop before K1 if this chunk is bad
-            unsigned int bad = 0;
-            CV_CUDA(cudaMemcpyAsync(&bad, idx->d_flag, sizeof(bad), cudaMemcpyDeviceToHost, s));
-            CV_CUDA(cudaStreamSynchronize(s));
-            if (bad) return fail(CV_ERR_NONFINITE, "embeddings contain %u NaN/Inf values", bad);
-        }
         int grid = static_cast<int>(std::min<int64_t>((m + 7) / 8, idx->sm_count * 8));
         k_normalise_append<<<grid, 256, 0, s>>>(a);
         CV_CUDA(cudaGetLastError());
         idx->launches.fetch_add(2);
         if (!on_device || lo + chunk_rows < n) CV_CUDA(cudaStreamSynchronize(s));  // staging buffers are reused
     }
-    unsigned int bad = 0;
-    CV_CUDA(cudaMemcpyAsync(&bad, idx->d_flag, sizeof(bad), cudaMemcpyDeviceToHost, s));
+    unsigned int flags[2] = {0, 0};
+    CV_CUDA(cudaMemcpyAsync(flags, idx->d_flag, sizeof(flags), cudaMemcpyDeviceToHost, s));
     CV_CUDA(cudaStreamSynchronize(s));
+    const unsigned int bad = flags[0];
+    if (flags[1]) idx->scale_bounded.store(false);  // (rows whose fp32 norm underflowed: K3 applies every scale from now on)
     if (bad) return fail(CV_ERR_NONFINITE, "embeddings contain %u NaN/Inf values; nothing was committed", bad);
     idx->n_committed.store(committed + appended, std::memory_order_release);
     idx->upserted.fetch_add(n);
@@ -773,25 +789,44 @@ int cv_query_device_exchange(cv_index* idx, const float* d_q, const cv_query_par
     return rc;
 }
 
-static int query_host(cv_index* idx, const float* q, const cv_query_params* p, const PeerExchange* px, uint64_t seq,
-                      float* out_scores, int64_t* out_rows, int32_t* out_counts) {
-    int rc = CV_OK;
-    const int B = p->n_queries, k = p->k;
+// A host-buffer query in two phases, so that a striped collection can put one batch in flight on every device
+// before waiting for any of them.
+struct PendingQuery {
+    cv_index* idx = nullptr;
+    QueryCtx* c = nullptr;
+    DoneFlag df{nullptr, 0, false, nullptr};
+    bool direct = false;
+    int B = 0, k = 0;
+    ~PendingQuery() {
+        if (idx && c) release_ctx(idx, c);
+    }
+};
+
+static int check_finite_queries(const cv_index* idx, const float* q, int B) {
     const size_t qn = static_cast<size_t>(B) * idx->D;
     for (size_t i = 0; i < qn; ++i) {
         uint32_t u;
         memcpy(&u, q + i, 4);
         if ((u & 0x7F800000u) == 0x7F800000u) return fail(CV_ERR_NONFINITE, "query %zu contains NaN/Inf", i / idx->D);
     }
+    return CV_OK;
+}
+
+// Phase 1: stage the queries / mask and enqueue the kernels on one of the index's query contexts.  Nothing blocks.
+static int query_host_begin(cv_index* idx, const float* q, const cv_query_params* p, const uint32_t* mask,
+                            const PeerExchange* px, uint64_t seq, PendingQuery* pend) {
+    int rc = CV_OK;
+    const int B = p->n_queries, k = p->k;
+    const size_t qn = static_cast<size_t>(B) * idx->D;
     DeviceGuard dg(idx->cfg.device);
     if (!dg.ok) return fail(CV_ERR_CUDA, "cudaSetDevice(%d) failed", idx->cfg.device);
-    std::shared_lock<std::shared_mutex> rd(idx->overwrite_mu);
+    std::shared_lock<std::shared_mutex> rd(idx->overwrite_mu);  // (an overwrite waits on every context's `busy` event)
     QueryCtx* c = nullptr;
     if ((rc = acquire_ctx(idx, &c))) return rc;
-    struct Releaser {
-        cv_index* i; QueryCtx* c;
-        ~Releaser() { release_ctx(i, c); }
-    } rel{idx, c};
+    pend->idx = idx;
+    pend->c = c;
+    pend->B = B;
+    pend->k = k;
     cudaStream_t s = c->stream;
     CV_CUDA(cudaStreamWaitEvent(s, c->busy, 0));
     if ((rc = c->d_q.reserve(qn)) || (rc = c->h_q.reserve(qn)) || (rc = c->d_out.reserve(static_cast<size_t>(B) * k)) ||
@@ -804,6 +839,7 @@ static int query_host(cv_index* idx, const float* q, const cv_query_params* p, c
     // addressing), the K2 tail raises a host-mapped flag, and this thread polls it.  Saves the two DMA
     // hand-offs and the interrupt-driven wake-up: ~50 us -> ~20 us end to end on a 10k-row collection.
     const bool direct = B <= 4 && idx->n_committed.load(std::memory_order_acquire) > 0;
+    pend->direct = direct;
     const float* q_arg = c->h_q.p;
     uint64_t* out_arg = c->h_out.p;
     if (!direct) {
@@ -812,27 +848,38 @@ static int query_host(cv_index* idx, const float* q, const cv_query_params* p, c
         out_arg = c->d_out.p;
     }
     if (c->ticket == 0) c->h_flag.p[0] = 0;  // fresh allocation
-    DoneFlag df{c->h_flag.p, ++c->ticket, false, c->h_q.p};
+    pend->df = DoneFlag{c->h_flag.p, ++c->ticket, false, c->h_q.p};
     const uint32_t* d_mask = nullptr;
-    if (p->mask) {
+    if (mask) {
         const int64_t n = idx->n_committed.load(std::memory_order_acquire);
         const size_t words = static_cast<size_t>((n + 31) / 32);
         if (words) {
             if ((rc = c->d_mask.reserve(words))) return rc;
-            CV_CUDA(cudaMemcpyAsync(c->d_mask.p, p->mask, words * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+            CV_CUDA(cudaMemcpyAsync(c->d_mask.p, mask, words * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
             d_mask = c->d_mask.p;
         }
     }
-    rc = enqueue_query(idx, c, s, q_arg, p, d_mask, out_arg, nullptr, 0, px, seq, direct ? &df : nullptr);
+    rc = enqueue_query(idx, c, s, q_arg, p, d_mask, out_arg, nullptr, 0, px, seq, direct ? &pend->df : nullptr);
     if (rc) { (void)cudaStreamSynchronize(s); return rc; }
     if (!direct) CV_CUDA(cudaMemcpyAsync(c->h_out.p, c->d_out.p, sizeof(uint64_t) * B * k, cudaMemcpyDeviceToHost, s));
     CV_CUDA(cudaEventRecord(c->busy, s));
-    if (df.armed) {
-        if ((rc = wait_done_flag(c->h_flag.p, df.value, s))) return rc;
+    return CV_OK;
+}
+
+// Phase 2: wait for the batch and decode its keys (all three outputs may be NULL: wait only).
+static int query_host_finish(PendingQuery* pend, float* out_scores, int64_t* out_rows, int32_t* out_counts) {
+    cv_index* idx = pend->idx;
+    QueryCtx* c = pend->c;
+    const int B = pend->B, k = pend->k;
+    DeviceGuard dg(idx->cfg.device);
+    if (!dg.ok) return fail(CV_ERR_CUDA, "cudaSetDevice(%d) failed", idx->cfg.device);
+    int rc;
+    if (pend->df.armed) {
+        if ((rc = wait_done_flag(c->h_flag.p, pend->df.value, c->stream))) return rc;
     } else {
-        CV_CUDA(cudaStreamSynchronize(s));
+        CV_CUDA(cudaStreamSynchronize(c->stream));
     }
-    cv_decode_keys(c->h_out.p, static_cast<int64_t>(B) * k, out_scores, out_rows);
+    if (out_scores || out_rows) cv_decode_keys(c->h_out.p, static_cast<int64_t>(B) * k, out_scores, out_rows);
     if (out_counts) {
         for (int b = 0; b < B; ++b) {
             int cnt = 0;
@@ -843,12 +890,36 @@ static int query_host(cv_index* idx, const float* q, const cv_query_params* p, c
     return CV_OK;
 }
 
+static int query_host(cv_index* idx, const float* q, const cv_query_params* p, const PeerExchange* px, uint64_t seq,
+                      float* out_scores, int64_t* out_rows, int32_t* out_counts) {
+    int rc = check_finite_queries(idx, q, p->n_queries);
+    if (rc) return rc;
+    PendingQuery pend;
+    if ((rc = query_host_begin(idx, q, p, p->mask, px, seq, &pend))) return rc;
+    return query_host_finish(&pend, out_scores, out_rows, out_counts);
+}
+
 int cv_query(cv_index* idx, const float* q, const cv_query_params* p, float* out_scores, int64_t* out_rows,
              int32_t* out_counts) {
     int rc = check_query_params(idx, q, p);
     if (rc) return rc;
     return query_host(idx, q, p, nullptr, 0, out_scores, out_rows, out_counts);
 }
+
+}  // extern "C"
+
+// G shards of one collection striped over the devices of THIS process (global row r lives on shard r % G at local
+// row r / G) and the peer-mapped exchange buffers their kernels trade per-GPU top-k through.
+struct cv_group {
+    std::vector<cv_index*> shards;
+    std::vector<uint64_t*> buffers;  // buffers[g]: exchange buffer in device g's memory, peer-mapped into every other device
+    int max_queries = 0, max_k = 0;
+    std::mutex mu;                   // one batch in flight per group: all shards see the same batches in the same order
+    uint64_t seq = 0;
+    bool broken = false;             // a shard failed mid-batch: its peers' flags can no longer be trusted
+};
+
+extern "C" {
 
 int cv_query_exchange(cv_index* idx, const float* q, const cv_query_params* p, const cv_peer_exchange* px, uint64_t seq,
                       float* out_scores, int64_t* out_rows, int32_t* out_counts) {
@@ -933,6 +1004,10 @@ int cv_load_rows(cv_index* idx, const uint16_t* bf16, const float* scale, const 
     DeviceGuard dg(idx->cfg.device);
     if (!dg.ok) return fail(CV_ERR_CUDA, "cudaSetDevice(%d) failed", idx->cfg.device);
     std::lock_guard<std::mutex> wg(idx->upsert_mu);
+    for (int64_t i = 0; i < n; ++i) {  // snapshots normally carry what cv_get_rows returned; anything else switches K3's prefilter off
+        const float sc = scale[i];
+        if (sc == sc && sc != 0.0f && !(sc - 1.0f <= 0.0078125f && 1.0f - sc <= 0.0078125f)) { idx->scale_bounded.store(false); break; }
+    }
     const int64_t base = idx->n_committed.load(std::memory_order_acquire);
     int rc = ensure_capacity(idx, base + n);
     if (rc) return rc;
@@ -977,6 +1052,162 @@ int cv_get_rows(cv_index* idx, const int64_t* rows, int64_t n, uint16_t* out_bf1
         i = j;
     }
     return CV_OK;
+}
+
+// Row-level edits that must be ordered against running queries exactly like an in-place overwrite: take the writer
+// locks, make the upsert stream wait for every query context, then write the few words.
+static int edit_rows_begin(cv_index* idx, const int64_t* rows, int64_t n, std::unique_lock<std::shared_mutex>& ow) {
+    const int64_t committed = idx->n_committed.load(std::memory_order_acquire);
+    for (int64_t i = 0; i < n; ++i)
+        if (rows[i] < 0 || rows[i] >= committed)
+            return fail(CV_ERR_INVALID, "row %lld out of range [0, %lld)", (long long)rows[i], (long long)committed);
+    ow.lock();
+    std::lock_guard<std::mutex> g(idx->ctx_mu);
+    for (auto& c : idx->ctx_all) CV_CUDA(cudaStreamWaitEvent(idx->upsert_stream, c->busy, 0));
+    return CV_OK;
+}
+
+int cv_delete_rows(cv_index* idx, const int64_t* rows, int64_t n) {
+    if (!idx || (!rows && n > 0) || n < 0) return fail(CV_ERR_INVALID, "bad argument");
+    if (n == 0) return CV_OK;
+    DeviceGuard dg(idx->cfg.device);
+    if (!dg.ok) return fail(CV_ERR_CUDA, "cudaSetDevice(%d) failed", idx->cfg.device);
+    std::lock_guard<std::mutex> wg(idx->upsert_mu);
+    std::unique_lock<std::shared_mutex> ow(idx->overwrite_mu, std::defer_lock);
+    int rc = edit_rows_begin(idx, rows, n, ow);
+    if (rc) return rc;
+    // a dead row keeps its slot (rows are dense) but carries scale = NaN: every kernel treats that as "not
+    // eligible", so deletes cost no per-query mask; an upsert into the slot revives it
+    static const uint32_t kNaN = 0x7FC00000u;
+    cudaStream_t s = idx->upsert_stream;
+    int64_t i = 0;
+    std::vector<uint32_t> run;
+    while (i < n) {
+        int64_t j = i + 1;
+        while (j < n && rows[j] == rows[j - 1] + 1) ++j;
+        run.assign(static_cast<size_t>(j - i), kNaN);
+        CV_CUDA(cudaMemcpyAsync(idx->scale.ptr<float>() + rows[i], run.data(), sizeof(uint32_t) * (j - i), cudaMemcpyHostToDevice, s));
+        CV_CUDA(cudaStreamSynchronize(s));  // `run` is reused
+        i = j;
+    }
+    return CV_OK;
+}
+
+int cv_set_codes(cv_index* idx, const int64_t* rows, const uint32_t* ns_codes, const uint32_t* label_codes, int64_t n) {
+    if (!idx || (!rows && n > 0) || n < 0) return fail(CV_ERR_INVALID, "bad argument");
+    if (n == 0 || (!ns_codes && !label_codes)) return CV_OK;
+    DeviceGuard dg(idx->cfg.device);
+    if (!dg.ok) return fail(CV_ERR_CUDA, "cudaSetDevice(%d) failed", idx->cfg.device);
+    std::lock_guard<std::mutex> wg(idx->upsert_mu);
+    std::unique_lock<std::shared_mutex> ow(idx->overwrite_mu, std::defer_lock);
+    int rc = edit_rows_begin(idx, rows, n, ow);
+    if (rc) return rc;
+    cudaStream_t s = idx->upsert_stream;
+    for (int64_t i = 0; i < n; ++i) {
+        if (ns_codes) CV_CUDA(cudaMemcpyAsync(idx->ns.ptr<uint32_t>() + rows[i], ns_codes + i, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+        if (label_codes) CV_CUDA(cudaMemcpyAsync(idx->label.ptr<uint32_t>() + rows[i], label_codes + i, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    }
+    CV_CUDA(cudaStreamSynchronize(s));
+    return CV_OK;
+}
+
+int cv_group_create(cv_index* const* shards, int32_t n_shards, int32_t max_queries, int32_t max_k, cv_group** out) {
+    if (!shards || !out) return fail(CV_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (n_shards < 2 || n_shards > CV_MAX_PEERS) return fail(CV_ERR_INVALID, "a group has 2..%d shards (got %d)", CV_MAX_PEERS, n_shards);
+    const int64_t bytes = cv_peer_exchange_bytes(n_shards, max_queries, max_k);
+    if (bytes < 0) return fail(CV_ERR_INVALID, "bad exchange capacity %d x %d", max_queries, max_k);
+    for (int g = 0; g < n_shards; ++g) {
+        if (!shards[g]) return fail(CV_ERR_INVALID, "shard %d is null", g);
+        if (shards[g]->D != shards[0]->D || shards[g]->cfg.metric != shards[0]->cfg.metric)
+            return fail(CV_ERR_INVALID, "shards disagree on dimension / metric");
+        if (shards[g]->row_stride != n_shards || shards[g]->cfg.row_offset != g)
+            return fail(CV_ERR_INVALID, "shard %d must be created with row_stride = %d and row_offset = %d", g, n_shards, g);
+    }
+    std::unique_ptr<cv_group> grp(new cv_group());
+    grp->shards.assign(shards, shards + n_shards);
+    grp->max_queries = max_queries;
+    grp->max_k = max_k;
+    // every device must be able to store into every other device's buffer
+    for (int a = 0; a < n_shards; ++a) {
+        const int da = shards[a]->cfg.device;
+        DeviceGuard dg(da);
+        if (!dg.ok) return fail(CV_ERR_CUDA, "cudaSetDevice(%d) failed", da);
+        for (int b = 0; b < n_shards; ++b) {
+            const int db = shards[b]->cfg.device;
+            if (da == db) continue;
+            int can = 0;
+            CV_CUDA(cudaDeviceCanAccessPeer(&can, da, db));
+            if (!can) return fail(CV_ERR_UNSUPPORTED, "device %d cannot map device %d's memory (no P2P): a striped collection needs NVLink / PCIe peer access", da, db);
+            cudaError_t e = cudaDeviceEnablePeerAccess(db, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                (void)cudaGetLastError();
+                return fail(CV_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d) failed: %s", da, db, cudaGetErrorString(e));
+            }
+            (void)cudaGetLastError();
+        }
+    }
+    for (int g = 0; g < n_shards; ++g) {
+        DeviceGuard dg(shards[g]->cfg.device);
+        void* p = nullptr;
+        CV_CUDA(cudaMalloc(&p, static_cast<size_t>(bytes)));
+        grp->buffers.push_back(static_cast<uint64_t*>(p));
+        CV_CUDA(cudaMemset(p, 0, static_cast<size_t>(bytes)));
+        CV_CUDA(cudaDeviceSynchronize());
+    }
+    *out = grp.release();
+    return CV_OK;
+}
+
+void cv_group_destroy(cv_group* grp) {
+    if (!grp) return;
+    for (size_t g = 0; g < grp->buffers.size(); ++g) {
+        DeviceGuard dg(grp->shards[g]->cfg.device);
+        (void)cudaDeviceSynchronize();
+        if (grp->buffers[g]) cudaFree(grp->buffers[g]);
+    }
+    delete grp;
+}
+
+int cv_group_query(cv_group* grp, const float* q, const cv_query_params* p, const uint32_t* const* masks, float* out_scores,
+                   int64_t* out_rows, int32_t* out_counts) {
+    if (!grp) return fail(CV_ERR_INVALID, "null group");
+    const int G = static_cast<int>(grp->shards.size());
+    int rc = check_query_params(grp->shards[0], q, p);
+    if (rc) return rc;
+    if (p->n_queries > grp->max_queries || p->k > grp->max_k)
+        return fail(CV_ERR_INVALID, "batch %d x k %d exceeds the group's exchange capacity %d x %d", p->n_queries, p->k,
+                    grp->max_queries, grp->max_k);
+    if ((rc = check_finite_queries(grp->shards[0], q, p->n_queries))) return rc;
+    std::lock_guard<std::mutex> lock(grp->mu);
+    if (grp->broken) return fail(CV_ERR_CUDA, "a shard of this striped collection failed earlier; the collection must be reopened");
+    const uint64_t seq = ++grp->seq;
+    std::vector<PendingQuery> pend(G);
+    // shard 0 last: it is the one whose merged result is read, and its kernel waits for everybody else's keys anyway
+    for (int i = 0; i < G; ++i) {
+        const int g = (i + 1) % G;
+        PeerExchange dx;
+        dx.world = G;
+        dx.rank = g;
+        dx.max_q = grp->max_queries;
+        dx.max_k = grp->max_k;
+        for (int j = 0; j < kMaxPeers; ++j) dx.base[j] = j < G ? grp->buffers[j] : nullptr;
+        rc = query_host_begin(grp->shards[g], q, p, masks ? masks[g] : nullptr, &dx, seq, &pend[g]);
+        if (rc) {
+            // the shards already launched are waiting for this one's keys: they give up after their bounded wait.
+            grp->broken = true;
+            return rc;
+        }
+    }
+    rc = query_host_finish(&pend[0], out_scores, out_rows, out_counts);
+    // every shard must be done before the next batch may reuse the exchange slots (they finish within microseconds
+    // of shard 0: all of them wait for the same flags)
+    for (int g = 1; g < G; ++g) {
+        const int r2 = query_host_finish(&pend[g], nullptr, nullptr, nullptr);
+        if (!rc) rc = r2;
+    }
+    if (rc) grp->broken = true;
+    return rc;
 }
 
 int cv_stats(cv_index* idx, cv_stats_t* out) {

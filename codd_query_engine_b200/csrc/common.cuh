@@ -269,6 +269,13 @@ __device__ __forceinline__ uint64_t ld_relaxed_sys(const uint64_t* p) {
     return v;
 }
 
+constexpr uint64_t kExchangeTimeoutNs = 30ull * 1000 * 1000 * 1000;
+__device__ __forceinline__ uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 // Whole block.  local[0..k) (shared memory, this GPU's final top-k for global query index q) is published
 // to all ranks; on return buf[0..k) holds the merged top-k of all ranks.  local may alias buf.
 __device__ __forceinline__ void exchange_and_merge(const PeerExchange& px, uint64_t seq, int q, const uint64_t* local,
@@ -289,7 +296,17 @@ __device__ __forceinline__ void exchange_and_merge(const PeerExchange& px, uint6
         st_release_sys(px.base[threadIdx.x] + static_cast<size_t>(px.rank) * px.max_q + q, seq);
     if (static_cast<int>(threadIdx.x) < G) {
         const uint64_t* f = px.base[px.rank] + static_cast<size_t>(threadIdx.x) * px.max_q + q;
-        while (ld_acquire_sys(f) < seq) {}
+        // bounded: a peer that never publishes (its launch failed, its process died) must not hang this GPU --
+        // after kExchangeTimeoutNs the kernel traps and the failure surfaces on the host as a CUDA error
+        uint64_t t0 = 0;
+        unsigned int spins = 0;
+        while (ld_acquire_sys(f) < seq) {
+            if ((++spins & 0xFFFu) == 0u) {
+                const uint64_t now = global_timer_ns();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > kExchangeTimeoutNs) __trap();
+            }
+        }
     }
     __syncthreads();
     // 3. merge the G lists that landed here

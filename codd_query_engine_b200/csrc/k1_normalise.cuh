@@ -25,6 +25,7 @@ struct NormArgs {
     float* scale;
     uint32_t* ns;
     uint32_t* label;
+    unsigned int* flags;       // flags[1] is raised when a stored scale is not 0 and not within 2^-7 of 1 (K3's prefilter bound)
 };
 
 __device__ __forceinline__ double warp_sum_f64(double v) {
@@ -62,7 +63,9 @@ __global__ void __launch_bounds__(256) k_normalise_append(NormArgs a) {
         }
         if (a.cosine) ss2 = warp_sum_f64(ss2);
         if (lane == 0) {
-            a.scale[dst] = a.cosine ? (ss2 > 0.0 ? static_cast<float>(1.0 / sqrt(ss2)) : 0.0f) : 1.0f;
+            const float sc = a.cosine ? (ss2 > 0.0 ? static_cast<float>(1.0 / sqrt(ss2)) : 0.0f) : 1.0f;
+            if (sc != 0.0f && !(fabsf(sc - 1.0f) <= 0.0078125f)) atomicOr(a.flags + 1, 1u);
+            a.scale[dst] = sc;
             a.ns[dst] = a.ns_in ? a.ns_in[i] : 0u;
             a.label[dst] = a.label_in ? a.label_in[i] : 0u;
         }

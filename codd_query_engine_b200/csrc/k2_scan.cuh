@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_topk(ScanArgs a) {
             const uint64_t sb = s_bound[my_b];
             thr = sb > thr ? sb : thr;
         }
-        const bool cand = owner && (FAST || DENSE || row_valid(my_row)) && key > thr;
+        const bool cand = owner && (FAST || DENSE || row_valid(my_row)) && sc == sc && key > thr;  // NaN scale = deleted row
         unsigned int pending = __ballot_sync(kFullMask, cand);
         while (pending) {
             const int src = __ffs(pending) - 1;
@@ -673,9 +673,10 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_topk_wide(ScanArgs a) 
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(kFullMask, acc[r], o);
             if (rows[r] >= 0) {  // warp-uniform
-                const float score = acc[r] * __ldg(a.scale + rows[r]);
+                const float sc = __ldg(a.scale + rows[r]);
+                const float score = acc[r] * sc;
                 const uint64_t key = pack_key(score, a.row_offset + static_cast<uint32_t>(rows[r]) * a.row_stride);
-                if (key > thr) {
+                if (sc == sc && key > thr) {  // NaN scale = deleted row
                     uint64_t kth;
                     if (warp_buf_append(my_list, cap, k, key, lane, cnt, kth) && kth > thr) thr = kth;
                     if (key > best) {

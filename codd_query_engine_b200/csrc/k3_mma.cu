@@ -1,818 +1,11 @@
-// k3_mma.cu -- K3 `gemm_topk`: batched scoring on the 5th-gen tensor cores with a fused top-k epilogue.
-//
-// Replaces the batched form of Collection.query (call site
-// codd_dal/metrics/metrics_semantic_metadata_store.py:314-316; chromadb accepts query batches) with an
-// exact scan:  S[q][row] = (Qhat_bf16[q] . E_bf16[row]) * scale[row], fp32 accumulate in TMEM.
-//
-// Shape of the work.  The query tile is the UMMA *M* operand (128 queries = 128 TMEM lanes, resident
-// in shared memory for the whole kernel), a tile of 128 corpus rows is the *N* operand (streamed once
-// from HBM by TMA, K-major, SWIZZLE_128B, 64-element K blocks through a 6-deep mbarrier ring), D is
-// the short K dimension (Dp/16 tcgen05.mma per tile).  With queries on the lanes every epilogue
-// thread owns ONE query: it keeps that query's running threshold in a register and its k-list
-// privately, so the fused top-k needs no atomics, no shuffles and no shared memory -- one FMUL +
-// one FSETP per score, and the B x N score matrix never leaves TMEM/registers.  The per-row scale
-// and the namespace / label / bitmask predicate are folded into one shared-memory vector per tile
-// (NaN = not eligible, so an ineligible score fails every comparison).
-//
-// Warp roles (192 threads, one CTA per SM, persistent): warp 0 = TMA producer (one elected lane),
-// warp 1 = TMEM allocator + MMA issuer (one elected lane), warps 2..5 = epilogue (TMEM lane quarter
-// = warp_id % 4).  Two TMEM accumulator stages (2 x 128 columns) overlap the MMAs of tile t+1 with the
-// epilogue of tile t.
-//
-// Roofline: algorithmic bytes = rows * (2*Dp + 4) per query tile pass, flops =
-// 2 * B * rows * Dp.  HBM-bound for B <~ 200, tensor-bound above.
-#include <cuda.h>
-#include <cuda_bf16.h>
-#include <cuda_runtime.h>
-
-#include <cstring>
-#include <mutex>
-#include <vector>
-
-#include "../../include/coddvec.h"
-#include "common.cuh"
-#include "k3_mma.cuh"
-#include "vmm.hpp"
+// k3_mma.cu -- host side of K3 `gemm_topk` (kernel: k3_kernel.cuh): shapes, scratch, tensor maps, launches.
+#include "k3_kernel.cuh"
 
 namespace cv {
 
+using namespace k3;
+
 namespace {
-
-constexpr int kQ = 128;          // queries per tile  (UMMA M, TMEM lanes)
-constexpr int kTN = 128;         // corpus rows per tile (UMMA N, TMEM columns per accumulator stage)
-constexpr int kKB = 64;          // K elements per shared-memory block = 128 bytes = one swizzle row
-constexpr int kBlockBytes = kTN * kKB * 2;  // 16 KiB: one [128 rows][64] bf16 block (Q or corpus)
-constexpr int kMaxStages = 8;    // corpus ring depth: as many 16 KiB stages as fit next to the query tile (<= 8)
-constexpr int kAccStages = 2;
-constexpr int kThreads = 192;
-constexpr int kMaxKBlocks = 64;  // Dp <= 4096 (CV_MAX_DIM)
-constexpr uint32_t kTmemCols = kAccStages * kTN;  // 256
-
-constexpr int kHeadsLd = 160;    // >= max CTAs per query tile (148), multiple of 4
-
-constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
-constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
-constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
-
-struct KArgs {
-    const float* scale;
-    const uint32_t* ns;
-    const uint32_t* label;
-    const uint32_t* mask;
-    uint32_t ns_code, label_code;
-    int64_t n;
-    int kblocks;
-    int stages;     // ring depth actually used (<= kMaxStages)
-    int q_resident; // 1: the query tile stays in shared memory for the whole kernel (short rows);
-                    // 0: its K blocks are streamed through the ring next to the corpus blocks (long rows)
-    int k;
-    uint32_t row_offset;
-    int n_tiles;
-    int q_tiles;
-    int P;          // CTAs sharing one query tile
-    int Bpad;
-    int B;            // real queries in this slice (lanes >= B are padding)
-    int smem_lists;   // k > 32: 1 = the per-query lists live in shared memory during the scan
-    uint64_t* lists;  // [P][Bpad][k]
-    uint32_t* gthr;   // [Bpad] shared per-query lower bounds on the k-th best score (ordered-float encoding)
-    uint32_t* heads;  // [Bpad][kHeadsLd] best score each CTA (slot p) has seen for the query, ordered floats, 0 = none
-    float* dump;      // debug: [Bpad][dump_ld] scores, or nullptr
-    int64_t dump_ld;
-    uint64_t corpus_hint;
-    uint32_t row_stride;   // global row = row_offset + local row * row_stride (1 = dense block, G = cyclic shard)
-    // fused query preparation (q_resident only): the CTA normalises its 128 raw queries itself and writes the bf16
-    // tile (and, with `split`, the bf16 residual tile) straight into the swizzled shared-memory layout
-    const float* q_raw;    // [B][D] fp32 raw queries of this slice, or nullptr (the tile comes from tmap_q)
-    int D;
-    int cosine;
-    int split;             // 1: Q = hi + lo (two bf16 tiles, two MMAs per K step) -> fp32-accurate scores
-    // fused tail (k <= 64): survivors above the cross-CTA bound are appended to cand[q][...]; the last CTA of a
-    // query-tile group merges them, writes out[] and resets gthr / heads / cnt / done for the next launch
-    int fused_tail;
-    uint64_t* cand;        // [Bpad][cand_ld]
-    int cand_ld;           // P * k
-    uint32_t* cnt;         // [Bpad] survivors appended per query
-    uint32_t* done;        // [q_tiles * CG] CTAs of the group that have published
-    uint64_t* out;         // [B][k] final keys of this slice
-};
-
-// ------------------------------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "CV_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra CV_DONE;\n\t"
-        "bra CV_WAIT;\n\t"
-        "CV_DONE:\n\t"
-        "}\n" ::"r"(bar), "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
-}
-// CG = 2: issued by both CTAs of the pair; the peer bit of the barrier address is cleared so that the
-// transaction bytes are counted on the LEADER's barrier (the MMA issuer waits there for both halves).
-template <int CG>
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, uint64_t hint) {
-    if (CG == 1) {
-        asm volatile(
-            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-            " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
-            "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "l"(hint)
-            : "memory");
-    } else {
-        asm volatile(
-            "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-            " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
-            "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "l"(hint)
-            : "memory");
-    }
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// arrive on the barrier at the same shared-memory offset in CTA `cta` of this cluster
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
-    asm volatile(
-        "{\n\t"
-        ".reg .b32 remote;\n\t"
-        "mapa.shared::cluster.u32 remote, %0, %1;\n\t"
-        "mbarrier.arrive.shared::cluster.b64 _, [remote];\n\t"
-        "}\n" ::"r"(bar), "r"(cta)
-        : "memory");
-}
-
-template <int CG>
-__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t cols) {
-    if (CG == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(cols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    } else {
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(cols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    }
-}
-template <int CG>
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-    if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc]^T, bf16 x bf16 -> fp32, issued by one thread for the CTA
-template <int CG>
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    if (CG == 1) {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "setp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-            "}\n" ::"r"(tmem_d),
-            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-            : "memory");
-    } else {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "setp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
-            "}\n" ::"r"(tmem_d),
-            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-            : "memory");
-    }
-}
-// arrive on an mbarrier when every tcgen05.mma issued so far by this thread has completed
-// (CG = 2: on the barrier at this offset in BOTH CTAs of the pair)
-template <int CG>
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    if (CG == 1) {
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-    } else {
-        const uint16_t mask = 3;
-        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-                     "h"(mask)
-                     : "memory");
-    }
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// UMMA shared-memory descriptor, K-major operand, SWIZZLE_128B, rows at a 128-byte pitch:
-//   bits [0,14) start address >> 4, [16,30) leading byte offset >> 4 (unused for swizzled K-major: 1),
-//   [32,46) stride byte offset >> 4 (8 rows * 128 B = 1024 B between 8-row core-matrix groups),
-//   [46,48) descriptor version = 1 (sm_100), [61,64) layout type = 2 (SWIZZLE_128B).
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
-    d |= static_cast<uint64_t>(1) << 16;
-    d |= static_cast<uint64_t>(1024 >> 4) << 32;
-    d |= static_cast<uint64_t>(1) << 46;
-    d |= static_cast<uint64_t>(2) << 61;
-    return d;
-}
-// Instruction descriptor for kind::f16: fp32 accumulate (bits 4-5 = 1), A = B = bf16 (bits 7-9, 10-12 = 1),
-// both K-major (bits 15, 16 = 0), N >> 3 at bits 17-22, M >> 4 at bits 24-28.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
-}
-
-// order-preserving float <-> uint32 (same mapping as the high word of a result key); 0 = "nothing yet"
-__device__ __forceinline__ uint32_t ord_of(float f) {
-    uint32_t u = __float_as_uint(f + 0.0f);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float ord_to_float(uint32_t o) {
-    return __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o);
-}
-// lower bound published by other CTAs -> strict threshold: s > result  <=>  s >= published score.
-// (The predecessor of +0.0 in the ordered encoding is -0.0, which compares EQUAL to +0.0 as a float and
-// would wrongly reject exact-zero ties, so it is skipped.)
-__device__ __forceinline__ float shared_threshold(uint32_t g) {
-    if (g <= 1u) return -INFINITY;
-    uint32_t o = g - 1u;
-    if (o == 0x7FFFFFFFu) o = 0x7FFFFFFEu;
-    return ord_to_float(o);
-}
-
-// ---- cross-CTA "heads" bound (k <= 32) -----------------------------------------------------------------
-// Every CTA scanning rows for query q publishes the BEST score it has seen in heads[q][p] (a plain store to
-// its own slot, no atomics).  The k-th largest of those heads is a lower bound on the global k-th best score
-// (k different CTAs each hold a distinct row at least that good) and -- because the global top-k rows are
-// almost surely spread over different CTAs -- a tight one.  Each epilogue thread recomputes it for its query
-// at tiles 1, 4, 16, 64, ... of its CTA; after the first refresh a CTA only sees candidates that would
-// also beat the other CTAs' best rows, instead of converging its own lists from -inf
-// (k*ln(rows_per_cta/k) list updates per CTA and query).
-// The bound actually computed is slightly weaker but needs no arrays: the P slots are cut into k contiguous
-// groups and the bound is the SMALLEST group maximum (k distinct CTAs still each hold a row at least that
-// good).  Loads go out 8 x 16 bytes at a time.
-__device__ __forceinline__ uint32_t heads_bound(const uint32_t* row, int P, int k) {
-    if (P < k) return 0u;
-    uint32_t m = 0u, bound = 0xFFFFFFFFu;
-    int g = 0;
-    const int nv = (P + 3) / 4;
-    if (nv >= k) {  // group boundaries at 16-byte granularity
-#pragma unroll 1
-        for (int v0 = 0; v0 < nv; v0 += 8) {
-            uint4 w[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-                w[u] = (v0 + u < nv) ? __ldcg(reinterpret_cast<const uint4*>(row) + v0 + u) : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                if (v0 + u < nv) {
-                    const int gv = (v0 + u) * k / nv;
-                    if (gv != g) { bound = min(bound, m); m = 0u; g = gv; }
-                    m = max(max(m, max(w[u].x, w[u].y)), max(w[u].z, w[u].w));
-                }
-            }
-        }
-    } else {  // few CTAs per query (pair mode, large batches): one slot at a time
-#pragma unroll 1
-        for (int s0 = 0; s0 < P; s0 += 8) {
-            uint32_t w[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) w[u] = (s0 + u < P) ? __ldcg(row + s0 + u) : 0u;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                if (s0 + u < P) {
-                    const int gv = (s0 + u) * k / P;
-                    if (gv != g) { bound = min(bound, m); m = 0u; g = gv; }
-                    m = max(m, w[u]);
-                }
-            }
-        }
-    }
-    return min(bound, m);
-}
-
-// register-resident descending list: branch-free bubble insertion, no memory traffic
-template <int KREG>
-__device__ __forceinline__ void list_insert_regs(uint64_t (&L)[KREG], uint64_t key) {
-    uint64_t cur = key;
-#pragma unroll
-    for (int j = 0; j < KREG; ++j) {
-        const bool gt = cur > L[j];
-        const uint64_t hi = gt ? cur : L[j];
-        cur = gt ? L[j] : cur;
-        L[j] = hi;
-    }
-}
-
-// v[j] for a runtime j without spilling v to local memory: a 31-select binary tree
-__device__ __forceinline__ uint32_t pick32(const uint32_t (&v)[32], int j) {
-    uint32_t a[16], b[8], c[4], d[2];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) a[i] = (j & 1) ? v[2 * i + 1] : v[2 * i];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) b[i] = (j & 2) ? a[2 * i + 1] : a[2 * i];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) c[i] = (j & 4) ? b[2 * i + 1] : b[2 * i];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) d[i] = (j & 8) ? c[2 * i + 1] : c[2 * i];
-    return (j & 16) ? d[1] : d[0];
-}
-
-// ------------------------------------------------------------------------------------------ query prep
-// Normalise fp32 queries exactly like the oracle (fp64 norm, fp32 divide), round to bf16, zero-pad to
-// [Bpad][Dp].  One warp per query row.  Only the long-row mode (query tile streamed through the ring by TMA)
-// needs this launch; short rows build their tile inside k_mma_topk (prep_query_tile).
-__global__ void __launch_bounds__(128) k_prep_queries(const float* q, int B, int Bpad, int D, int Dp, int cosine,
-                                                      __nv_bfloat16* out) {
-    const int lane = threadIdx.x & 31;
-    const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (row >= Bpad) return;
-    __nv_bfloat16* o = out + static_cast<size_t>(row) * Dp;
-    if (row >= B) {
-        for (int d = lane; d < Dp; d += 32) o[d] = __float2bfloat16_rn(0.0f);
-        return;
-    }
-    const float* r = q + static_cast<size_t>(row) * D;
-    float safe = 1.0f;
-    if (cosine) {
-        double ss = 0.0;
-        for (int d = lane; d < D; d += 32) {
-            double v = static_cast<double>(r[d]);
-            ss += v * v;
-        }
-#pragma unroll
-        for (int o2 = 16; o2 > 0; o2 >>= 1) ss += __shfl_xor_sync(kFullMask, ss, o2);
-        float nrm = static_cast<float>(sqrt(ss));
-        safe = nrm > 0.0f ? nrm : 1.0f;
-    }
-    for (int d = lane; d < Dp; d += 32) o[d] = __float2bfloat16_rn(d < D ? __fdiv_rn(r[d], safe) : 0.0f);
-}
-
-// Fused query preparation: the whole CTA turns its kQ raw fp32 queries into the bf16 UMMA operand tile in
-// shared memory -- normalised exactly like the oracle (fp64 norm, fp32 divide), rounded to bf16, laid out as the
-// TMA would have written it: K block kb = 16 KiB of [128 rows][64 elements], 128-byte rows, 16-byte chunk cc of
-// row r stored at chunk position cc ^ (r & 7) (SWIZZLE_128B; block bases are 1024-byte aligned).  With `split`
-// a second tile holds bf16(qhat - hi): hi + lo carries 16 mantissa bits, so the two MMAs per K step reproduce
-// the fp32 query to ~2^-17 relative.  Rows past B and elements past D are zero.  One warp per row; lane l owns
-// the 16-byte chunks l and l + 32 (rows of up to 512 elements stay resident, see mma_enqueue).
-__device__ __forceinline__ void prep_query_tile(unsigned char* sm_q, const float* q_raw, int q_row0, int B, int D,
-                                                int kblocks, int cosine, int split) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nchunks = kblocks * 8;
-    const bool vec = (D & 3) == 0 && (reinterpret_cast<uintptr_t>(q_raw) & 15) == 0;
-    for (int r = warp; r < kQ; r += kThreads / 32) {
-        const int qg = q_row0 + r;
-        const bool live = qg < B;  // warp-uniform
-        const float* src = q_raw + static_cast<size_t>(live ? qg : 0) * D;
-        float x[2][8];
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int d0 = (lane + 32 * j) * 8;
-            if (live && vec && d0 + 8 <= D) {
-                const float4 u = __ldg(reinterpret_cast<const float4*>(src + d0));
-                const float4 w = __ldg(reinterpret_cast<const float4*>(src + d0 + 4));
-                x[j][0] = u.x; x[j][1] = u.y; x[j][2] = u.z; x[j][3] = u.w;
-                x[j][4] = w.x; x[j][5] = w.y; x[j][6] = w.z; x[j][7] = w.w;
-            } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) x[j][e] = (live && d0 + e < D) ? __ldg(src + d0 + e) : 0.0f;
-            }
-        }
-        float safe = 1.0f;
-        if (cosine && live) {
-            double ss = 0.0;
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
-#pragma unroll
-                for (int e = 0; e < 8; ++e) ss += static_cast<double>(x[j][e]) * static_cast<double>(x[j][e]);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(kFullMask, ss, o);
-            const float nrm = static_cast<float>(sqrt(ss));
-            safe = nrm > 0.0f ? nrm : 1.0f;
-        }
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int c = lane + 32 * j;
-            if (c < nchunks) {
-                uint32_t hi[4], lo[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float v0 = __fdiv_rn(x[j][2 * e], safe), v1 = __fdiv_rn(x[j][2 * e + 1], safe);
-                    const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
-                    hi[e] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
-                    const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
-                    const __nv_bfloat16 l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
-                    lo[e] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
-                }
-                const int kb = c >> 3, cc = c & 7;
-                unsigned char* dst = sm_q + static_cast<size_t>(kb) * kBlockBytes + r * 128 + ((cc ^ (r & 7)) << 4);
-                *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                if (split)
-                    *reinterpret_cast<uint4*>(dst + static_cast<size_t>(kblocks) * kBlockBytes) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            }
-        }
-    }
-    fence_proxy_async();  // generic-proxy stores above -> visible to the tensor core's async-proxy reads
-}
-
-// ------------------------------------------------------------------------------------------ main kernel
-// CG = 1: one CTA per SM works alone (M = 128 queries, N = 128 corpus rows per tile).
-// CG = 2: a CTA pair (cluster of 2, `cta_group::2`) shares every MMA: M = 256 queries (128 per CTA),
-//         N = 256 corpus rows per tile of which each CTA stages 128 -- so each SM reads half the B
-//         operand from its shared memory and L2 serves each corpus tile once per 256 queries.
-//         Only the leader CTA (cluster rank 0) issues MMAs; both CTAs' TMA loads complete on the
-//         leader's `full` barrier; `tcgen05.commit ... multicast` releases ring slots / publishes
-//         accumulators in both CTAs; the peer's epilogue warps arrive remotely on the leader's
-//         `tmem_empty` barrier.
-template <bool DUMP, int KREG, int CG>
-__global__ void __launch_bounds__(kThreads, 1)
-k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_e, const KArgs a) {
-    constexpr int TN = kTN * CG;                       // corpus rows (= accumulator columns) per tile
-    constexpr uint32_t kCols = kAccStages * TN;        // TMEM columns: 256 (CG=1) / 512 (CG=2)
-    extern __shared__ __align__(1024) unsigned char smem[];
-    // carve-up (all block bases 1024-byte aligned, as SWIZZLE_128B requires)
-    // q_resident: [query tile: kblocks (x2 when split) x 16 KiB][ring: stages x 16 KiB corpus blocks]
-    // streamed:   [ring: stages x (16 KiB query block + 16 KiB corpus block)]
-    const bool qres = a.q_resident != 0;
-    const int kStages = a.stages;
-    const uint32_t stage_bytes = qres ? kBlockBytes : 2 * kBlockBytes;
-    unsigned char* sm_q = smem;
-    const int qblocks = a.kblocks * (a.split ? 2 : 1);  // resident query tile: hi blocks, then the residual (lo) blocks
-    unsigned char* sm_ring = smem + (qres ? static_cast<size_t>(qblocks) * kBlockBytes : 0);
-    float* sm_scale = reinterpret_cast<float*>(sm_ring + static_cast<size_t>(kStages) * stage_bytes);  // [2][TN]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sm_scale + kAccStages * TN);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1 + 2 * kAccStages);
-    uint64_t* sm_lists = reinterpret_cast<uint64_t*>(tmem_slot + 4);  // [128][k] when a.smem_lists
-
-    const uint32_t bar_full = smem_u32(bars);                  // [kMaxStages] (leader's are the live ones)
-    const uint32_t bar_empty = bar_full + 8 * kMaxStages;      // [kMaxStages]
-    const uint32_t bar_q = bar_empty + 8 * kMaxStages;         // [1]
-    const uint32_t bar_tfull = bar_q + 8;                      // [kAccStages]
-    const uint32_t bar_tempty = bar_tfull + 8 * kAccStages;    // [kAccStages] (leader's are the live ones)
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;   // 0 = leader
-    const int unit = blockIdx.x / CG;                         // CTA (CG=1) or CTA pair (CG=2)
-    const int qt = unit % a.q_tiles;                          // query tile of 128*CG queries
-    const int p = unit / a.q_tiles;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) {
-            mbar_init(bar_full + 8 * s, CG);      // own arrive.expect_tx (+ the peer's remote arrive)
-            mbar_init(bar_empty + 8 * s, 1);      // one tcgen05.commit
-        }
-        mbar_init(bar_q, CG);
-        for (int s = 0; s < kAccStages; ++s) {
-            mbar_init(bar_tfull + 8 * s, 1);
-            mbar_init(bar_tempty + 8 * s, 4 * CG);  // one arrival per epilogue warp of every CTA in the group
-        }
-        fence_barrier_init();
-        fence_proxy_async();
-    }
-    if (warp == 1) tmem_alloc<CG>(smem_u32(tmem_slot), kCols);
-    const bool fused_prep = a.q_raw != nullptr;  // (q_resident only)
-    if (fused_prep)
-        prep_query_tile(sm_q, a.q_raw, (qt * CG + static_cast<int>(rank)) * kQ, a.B, a.D, a.kblocks, a.cosine, a.split);
-    tc_fence_before();
-    if (CG == 2) cluster_sync(); else __syncthreads();  // barriers, TMEM address and both CTAs' query tiles are ready
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        // ===================================================================== TMA producer (every CTA)
-        if (lane == 0) {
-            if (!fused_prep) tma_prefetch_desc(&tmap_q);
-            tma_prefetch_desc(&tmap_e);
-            const int q_row = (qt * CG + static_cast<int>(rank)) * kQ;
-            if (qres && !fused_prep) {
-                const uint32_t q_bytes = static_cast<uint32_t>(a.kblocks) * kBlockBytes;
-                if (rank == 0) mbar_arrive_expect_tx(bar_q, q_bytes * CG);
-                else mbar_arrive_cluster(bar_q, 0);
-                for (int kb = 0; kb < a.kblocks; ++kb)
-                    tma_load_2d<CG>(smem_u32(sm_q + static_cast<size_t>(kb) * kBlockBytes), &tmap_q, bar_q, kb * kKB, q_row,
-                                    kEvictLast);
-            }
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int t = p; t < a.n_tiles; t += a.P) {
-                for (int kb = 0; kb < a.kblocks; ++kb) {
-                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                    if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, stage_bytes * CG);
-                    else mbar_arrive_cluster(bar_full + 8 * stage, 0);
-                    unsigned char* slot = sm_ring + static_cast<size_t>(stage) * stage_bytes;
-                    if (!qres) {  // this K block of the query tile rides along (L2 resident, evict-last)
-                        tma_load_2d<CG>(smem_u32(slot), &tmap_q, bar_full + 8 * stage, kb * kKB, q_row, kEvictLast);
-                        slot += kBlockBytes;
-                    }
-                    tma_load_2d<CG>(smem_u32(slot), &tmap_e, bar_full + 8 * stage, kb * kKB,
-                                    t * TN + static_cast<int>(rank) * kTN, a.corpus_hint);
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ===================================================================== MMA issuer (leader CTA only)
-        if (lane == 0 && rank == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(kQ * CG, TN);
-            if (qres && !fused_prep) {
-                mbar_wait(bar_q, 0);
-                tc_fence_after();
-            }
-            int stage = 0, as = 0;
-            uint32_t phase = 0, aphase = 0;
-            for (int t = p; t < a.n_tiles; t += a.P) {
-                mbar_wait(bar_tempty + 8 * as, aphase ^ 1);  // every epilogue warp has drained this accumulator stage
-                tc_fence_after();
-                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * TN);
-                for (int kb = 0; kb < a.kblocks; ++kb) {
-                    mbar_wait(bar_full + 8 * stage, phase);  // TMA bytes of every CTA in the group have landed
-                    tc_fence_after();
-                    const uint32_t slot = smem_u32(sm_ring + static_cast<size_t>(stage) * stage_bytes);
-                    const uint32_t a_addr = qres ? smem_u32(sm_q + static_cast<size_t>(kb) * kBlockBytes) : slot;
-                    const uint32_t b_addr = qres ? slot : slot + kBlockBytes;
-#pragma unroll
-                    for (int ks = 0; ks < kKB / 16; ++ks)  // UMMA_K = 16 bf16 = 32 bytes inside the swizzle row
-                        umma_bf16<CG>(tmem_d, umma_desc_sw128(a_addr + ks * 32), umma_desc_sw128(b_addr + ks * 32), idesc,
-                                      (kb | ks) != 0 ? 1u : 0u);
-                    if (a.split) {  // + (residual query tile) x (the same corpus block)
-                        const uint32_t lo_addr = a_addr + static_cast<uint32_t>(a.kblocks) * kBlockBytes;
-#pragma unroll
-                        for (int ks = 0; ks < kKB / 16; ++ks)
-                            umma_bf16<CG>(tmem_d, umma_desc_sw128(lo_addr + ks * 32), umma_desc_sw128(b_addr + ks * 32), idesc, 1u);
-                    }
-                    umma_commit<CG>(bar_empty + 8 * stage);  // frees the ring slot (in both CTAs) once read
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
-                }
-                umma_commit<CG>(bar_tfull + 8 * as);  // accumulator complete -> epilogue warps (of both CTAs)
-                if (++as == kAccStages) { as = 0; aphase ^= 1; }
-            }
-        }
-    } else {
-        // ===================================================================== epilogue (128 threads per CTA)
-        const int et = threadIdx.x - 64;                 // 0..127
-        const int qlane = 32 * (warp & 3) + lane;        // TMEM lane = query within this CTA's 128
-        const int qglobal = (qt * CG + static_cast<int>(rank)) * kQ + qlane;
-        const bool fused_tail = KREG > 0 && a.fused_tail != 0;
-        uint64_t* const glist = fused_tail ? nullptr : a.lists + (static_cast<size_t>(p) * a.Bpad + qglobal) * a.k;
-        // large k (KREG == 0): the working list is in shared memory when it fits (fast warp-cooperative
-        // insertion), else directly in global memory; lanes of a warp own consecutive lists either way
-        uint64_t* list = (KREG == 0 && a.smem_lists) ? sm_lists + static_cast<size_t>(qlane) * a.k : glist;
-        constexpr int KR = KREG > 0 ? KREG : 1;
-        // k <= KREG: the list lives in registers, right-aligned -- slots [KREG-k, KREG) hold the top-k
-        // descending, the slots before them are never-beaten sentinels -- so the k-th best is always
-        // L[KREG-1] (a compile-time register, no dynamic indexing).
-        uint64_t L[KR];
-#pragma unroll
-        for (int j = 0; j < KR; ++j) L[j] = (j < KR - a.k) ? ~0ull : 0ull;
-        if (KREG == 0) {
-            for (int j = 0; j < a.k; ++j) list[j] = 0ull;
-            __syncwarp();
-        }
-        const bool live = qglobal < a.B;           // padding lanes never produce candidates
-        const bool share = a.P > 1 && live;        // CTAs scanning other rows for the same query trade thresholds
-        float thr_local = live ? -INFINITY : INFINITY;
-        float thr = thr_local;
-        const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(32 * (warp & 3)) << 16);
-        const bool pred = a.mask != nullptr || a.ns_code != kAny || a.label_code != kAny;
-        int as = 0;
-        uint32_t aphase = 0;
-        // scale * eligibility of one tile row (NaN = skip); loaded one tile ahead so that the L2/HBM latency
-        // of these small loads is never on the epilogue's critical path
-        auto row_scale = [&](int t, int h) -> float {
-            const int64_t row = static_cast<int64_t>(t) * TN + h * kTN + et;
-            float sc = __int_as_float(0x7FC00000);
-            if (t < a.n_tiles && row < a.n) {
-                bool ok = true;
-                if (pred) {
-                    if (a.ns_code != kAny) ok = __ldg(a.ns + row) == a.ns_code;
-                    if (ok && a.label_code != kAny) ok = __ldg(a.label + row) == a.label_code;
-                    if (ok && a.mask) ok = (__ldg(a.mask + (row >> 5)) >> (row & 31)) & 1u;
-                }
-                if (ok) sc = __ldg(a.scale + row);
-            }
-            return sc;
-        };
-        uint32_t* const head_row = a.heads + static_cast<size_t>(qglobal) * kHeadsLd;
-        float best_local = -INFINITY;  // best score this thread has inserted (its CTA's head for this query)
-        int tcount = 0, next_refresh = 1;
-        const int my_tiles = (a.n_tiles - p + a.P - 1) / a.P;  // tiles this CTA processes
-        float sc_next[CG];
-#pragma unroll
-        for (int h = 0; h < CG; ++h) sc_next[h] = row_scale(p, h);
-        uint32_t g_next = share ? __ldcg(a.gthr + qglobal) : 0u;
-        for (int t = p; t < a.n_tiles; t += a.P) {
-#pragma unroll
-            for (int h = 0; h < CG; ++h) sm_scale[as * TN + h * kTN + et] = sc_next[h];
-            if (share) thr = fmaxf(thr, fmaxf(thr_local, shared_threshold(g_next)));
-            if (KREG > 0 && share && tcount == next_refresh) {  // tiles 1, 4, 16, 64, ... of this CTA
-                if (tcount * 8 <= my_tiles)  // (not worth the L2 round trips when the CTA is almost done)
-                    thr = fmaxf(thr, shared_threshold(heads_bound(head_row, a.P, a.k)));
-                next_refresh *= 4;
-            }
-            ++tcount;
-            // prefetch for the next tile of this CTA (in flight while this tile is processed)
-#pragma unroll
-            for (int h = 0; h < CG; ++h) sc_next[h] = row_scale(t + a.P, h);
-            if (share) g_next = __ldcg(a.gthr + qglobal);
-            asm volatile("bar.sync 1, 128;" ::: "memory");  // this CTA's epilogue warps only
-            mbar_wait(bar_tfull + 8 * as, aphase);
-            tc_fence_after();
-            const float* sc_tile = sm_scale + as * TN;
-            const uint32_t lrow0 = static_cast<uint32_t>(t) * TN;  // local row of the tile's first column
-#pragma unroll 1
-            for (int c = 0; c < TN / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld32(lane_base + static_cast<uint32_t>(as * TN + c * 32), v);
-                tmem_ld_wait();
-                bool any = false;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float s = __uint_as_float(v[j]) * sc_tile[c * 32 + j];
-                    v[j] = __float_as_uint(s);
-                    any |= s > thr;
-                }
-                if (DUMP) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int64_t row = static_cast<int64_t>(t) * TN + c * 32 + j;
-                        if (row < a.n) a.dump[static_cast<size_t>(qglobal) * a.dump_ld + row] = __uint_as_float(v[j]);
-                    }
-                }
-                if (KREG > 0) {
-                    if (any) {
-                        // rare: build the candidate bitmap, then handle candidates one at a time through a
-                        // single inlined insertion site (keeps the list in registers, keeps the code small)
-                        uint32_t cand = 0;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) cand |= (__uint_as_float(v[j]) > thr) ? (1u << j) : 0u;
-                        bool changed = false;
-                        while (cand) {
-                            const int j = __ffs(cand) - 1;
-                            cand &= cand - 1;
-                            const float s = __uint_as_float(pick32(v, j));
-                            if (s > thr) {  // thr may have risen since the bitmap was built
-                                list_insert_regs<KR>(L, pack_key(s, a.row_offset + (lrow0 + c * 32 + j) * a.row_stride));
-                                if (L[KR - 1] != 0ull) thr_local = key_score(L[KR - 1]);
-                                thr = fmaxf(thr, thr_local);
-                                if (share && s > best_local) {  // publish this CTA's new head for the query
-                                    best_local = s;
-                                    __stcg(head_row + p, ord_of(s));
-                                }
-                                changed = true;
-                            }
-                        }
-                        if (changed && share && L[KR - 1] != 0ull) atomicMax(a.gthr + qglobal, ord_of(thr_local));
-                    }
-                } else if (__any_sync(kFullMask, any)) {
-                    // large k: the lists live in global memory (L1/L2 resident) and the whole warp inserts
-                    // one candidate at a time (warp_list_insert: ballot-located position, parallel shift)
-                    uint32_t cand = 0;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) cand |= (__uint_as_float(v[j]) > thr) ? (1u << j) : 0u;
-                    uint32_t owners = __ballot_sync(kFullMask, cand != 0u);
-                    while (owners) {
-                        const int src = __ffs(owners) - 1;
-                        owners &= owners - 1;
-                        uint32_t cm = __shfl_sync(kFullMask, cand, src);
-                        float thr_src = __shfl_sync(kFullMask, thr, src);
-                        float local_src = __shfl_sync(kFullMask, thr_local, src);
-                        uint64_t* lst = list + static_cast<ptrdiff_t>(src - lane) * a.k;  // src lane's list
-                        bool changed = false;
-                        while (cm) {
-                            const int j = __ffs(cm) - 1;
-                            cm &= cm - 1;
-                            const float s = __shfl_sync(kFullMask, __uint_as_float(pick32(v, j)), src);
-                            if (s > thr_src) {
-                                const uint64_t kth =
-                                    warp_list_insert(lst, a.k, pack_key(s, a.row_offset + (lrow0 + c * 32 + j) * a.row_stride), lane);
-                                if (kth != 0ull) local_src = key_score(kth);
-                                thr_src = fmaxf(thr_src, local_src);
-                                changed = true;
-                            }
-                        }
-                        if (lane == src && changed) {
-                            thr_local = local_src;
-                            thr = thr_src;
-                            if (share && local_src > -INFINITY) atomicMax(a.gthr + qglobal, ord_of(local_src));
-                        }
-                    }
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                if (rank == 0) mbar_arrive(bar_tempty + 8 * as);
-                else mbar_arrive_cluster(bar_tempty + 8 * as, 0);
-            }
-            if (++as == kAccStages) { as = 0; aphase ^= 1; }
-        }
-        if (fused_tail) {
-            // ---- fused tail: no merge launch.  P == 1: this list is final.  Otherwise publish the keys that can
-            // still be in the global top-k -- score >= max(largest k-th best any CTA reached, heads bound): both are
-            // lower bounds on the global k-th best score, so every global top-k key survives in its CTA -- to
-            // cand[q][...] (one atomicAdd per query reserves the range; ~k ln k keys per query in the whole grid),
-            // and let the last CTA of the group (threadfence + counter) merge its 128 queries, thread = query.
-            if (a.P == 1) {
-                if (live) {
-#pragma unroll
-                    for (int j = 0; j < KR; ++j)
-                        if (j >= KR - a.k) a.out[static_cast<size_t>(qglobal) * a.k + (j - (KR - a.k))] = L[j];
-                }
-            } else {
-                __shared__ int s_last;
-                const int group = qt * CG + static_cast<int>(rank);
-                if (live) {
-                    const uint32_t g = max(__ldcg(a.gthr + qglobal), heads_bound(head_row, a.P, a.k));
-                    int ns = 0;
-#pragma unroll
-                    for (int j = 0; j < KR; ++j)
-                        ns += (j >= KR - a.k && L[j] != 0ull && static_cast<uint32_t>(L[j] >> 32) >= g) ? 1 : 0;
-                    if (ns) {  // the list is sorted: the survivors are its first ns entries
-                        const uint32_t pos = atomicAdd(a.cnt + qglobal, static_cast<uint32_t>(ns));
-                        uint64_t* dst = a.cand + static_cast<size_t>(qglobal) * a.cand_ld + pos;
-#pragma unroll
-                        for (int j = 0; j < KR; ++j) {
-                            const int i = j - (KR - a.k);
-                            if (i >= 0 && i < ns) __stcg(dst + i, L[j]);
-                        }
-                    }
-                }
-                __threadfence();
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (et == 0) s_last = atomicAdd(a.done + group, 1u) == static_cast<unsigned>(a.P - 1) ? 1 : 0;
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (s_last) {
-                    __threadfence();
-                    if (live) {
-                        const uint32_t m = __ldcg(a.cnt + qglobal);
-                        const uint64_t* src = a.cand + static_cast<size_t>(qglobal) * a.cand_ld;
-#pragma unroll
-                        for (int j = 0; j < KR; ++j) L[j] = (j < KR - a.k) ? ~0ull : 0ull;
-#pragma unroll 1
-                        for (uint32_t i0 = 0; i0 < m; i0 += 8) {
-                            uint64_t kk[8];
-#pragma unroll
-                            for (int u = 0; u < 8; ++u) kk[u] = (i0 + u < m) ? __ldcg(src + i0 + u) : 0ull;
-#pragma unroll
-                            for (int u = 0; u < 8; ++u)
-                                if (kk[u] > L[KR - 1]) list_insert_regs<KR>(L, kk[u]);
-                        }
-#pragma unroll
-                        for (int j = 0; j < KR; ++j)
-                            if (j >= KR - a.k) a.out[static_cast<size_t>(qglobal) * a.k + (j - (KR - a.k))] = L[j];
-                        // every CTA of the group is done: leave the shared state zero for the next launch
-                        a.cnt[qglobal] = 0u;
-                        a.gthr[qglobal] = 0u;
-                        for (int v = 0; v < (a.P + 3) / 4; ++v) reinterpret_cast<uint4*>(head_row)[v] = make_uint4(0u, 0u, 0u, 0u);
-                    }
-                    if (et == 0) a.done[group] = 0u;
-                }
-            }
-        } else if (KREG > 0) {
-#pragma unroll
-            for (int j = 0; j < KR; ++j)
-                if (j >= KR - a.k) glist[j - (KR - a.k)] = L[j];
-        } else if (a.smem_lists) {
-            __syncwarp();
-            for (int j = 0; j < a.k; ++j) glist[j] = list[j];
-        }
-    }
-    tc_fence_before();
-    if (CG == 2) cluster_sync(); else __syncthreads();  // nobody leaves while its partner may still touch it
-    if (warp == 1) {
-        tc_fence_after();
-        tmem_dealloc<CG>(tmem_base, kCols);
-    }
-}
 
 constexpr size_t kSmemLimit = 232448;  // 227 KiB: the per-CTA maximum on sm_100
 
@@ -827,17 +20,6 @@ int mma_stages(int qblocks, int cg, size_t list_bytes, bool q_resident) {
     int s = kMaxStages;
     while (s > 1 && mma_smem_bytes(qblocks, s, cg, list_bytes, q_resident) > kSmemLimit) --s;
     return s;
-}
-
-using MmaKernel = void (*)(const CUtensorMap, const CUtensorMap, const KArgs);
-
-template <int CG>
-MmaKernel pick_mma_kernel(bool dump, int k) {
-    if (dump) return k_mma_topk<true, 0, CG>;
-    if (k <= 16) return k_mma_topk<false, 16, CG>;
-    if (k <= 32) return k_mma_topk<false, 32, CG>;
-    if (k <= 64) return k_mma_topk<false, 64, CG>;
-    return k_mma_topk<false, 0, CG>;
 }
 
 thread_local std::string g_mma_err;
@@ -894,7 +76,7 @@ int raise_smem_limit(MmaKernel kernel) {
 // All of it is zero between launches (the fused tail's last CTA per group clears what its group dirtied), so it is
 // zeroed once, when (re)allocated.
 size_t mma_state_bytes(int queries) {
-    return (static_cast<size_t>(queries) * (kHeadsLd + 2) + static_cast<size_t>(queries) / kQ + 4) * sizeof(uint32_t);
+    return ((static_cast<size_t>(queries) * (kHeadsLd + 2) + static_cast<size_t>(queries) / kQ + 4) * sizeof(uint32_t) + 63) / 64 * 64;
 }
 
 int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* launches) {
@@ -930,9 +112,16 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
     const size_t smem = mma_smem_bytes(qblocks, stages, cg, smem_list_bytes, q_resident);
     if (smem > kSmemLimit)
         return mma_fail(CV_ERR_UNSUPPORTED, "tensor-core path: query tile does not fit shared memory at dim " + std::to_string(m.Dp));
-    const bool fused_prep = q_resident && kblocks <= 8;     // prep_query_tile: lanes own chunks l and l + 32
-    const bool fused_tail = m.k <= 64 && m.dump == nullptr;  // register-resident lists
-    MmaKernel kernel = cg == 2 ? pick_mma_kernel<2>(m.dump != nullptr, m.k) : pick_mma_kernel<1>(m.dump != nullptr, m.k);
+    // (CODDVEC_K3_SPLIT_LAUNCHES: bit 0 = separate query-prep launch, bit 1 = separate merge launch -- A/B switches)
+    static const int split_launches = getenv("CODDVEC_K3_SPLIT_LAUNCHES") ? atoi(getenv("CODDVEC_K3_SPLIT_LAUNCHES")) : 0;
+    const bool fused_prep = q_resident && kblocks <= 8 && (split || !(split_launches & 1));  // prep_query_tile: lanes own chunks l, l + 32
+    const bool fused_tail = m.k <= 64 && m.dump == nullptr && !(split_launches & 2);          // register-resident lists
+    // (CODDVEC_K3_EW=4: four epilogue warps where both variants are built, k in 11..16 -- an A/B switch)
+    static const int ew_pref = getenv("CODDVEC_K3_EW") ? atoi(getenv("CODDVEC_K3_EW")) : 8;
+    const bool dump = m.dump != nullptr;
+    MmaKernel kernel = cg == 2 ? pick_mma_kernel_cg2(dump, m.k, ew_pref) : pick_mma_kernel<1>(dump, m.k, ew_pref);
+    const int ew = mma_kernel_epilogue_warps(dump, m.k, ew_pref);
+    const int halves = ew / 4;  // list owners per (CTA, query)
     int rc;
     if ((rc = raise_smem_limit(kernel))) return rc;
     // batches larger than one wave of query tiles are processed in slices (stream order keeps the scratch safe)
@@ -946,7 +135,7 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
         if (P < 1) P = 1;
         // work scratch (contents do not matter between launches): [bf16 queries Bpad x Dp (long rows only)][keys Bpad x P x k]
         const size_t q_bytes = fused_prep ? 0 : (static_cast<size_t>(Bpad) * m.Dp * 2 + 1023) / 1024 * 1024;
-        const size_t list_bytes = static_cast<size_t>(P) * Bpad * m.k * sizeof(uint64_t);
+        const size_t list_bytes = static_cast<size_t>(P) * halves * Bpad * m.k * sizeof(uint64_t);
         const size_t need = q_bytes + list_bytes;
         if (need > scratch.cap) {
             MMA_CUDA(cudaStreamSynchronize(m.stream));
@@ -962,8 +151,8 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
             scratch.state = nullptr;
             scratch.state_q = 0;
             const int cap_q = std::max(Bpad, 1024);
-            MMA_CUDA(cudaMalloc(&scratch.state, mma_state_bytes(cap_q)));
-            MMA_CUDA(cudaMemsetAsync(scratch.state, 0, mma_state_bytes(cap_q), m.stream));
+            MMA_CUDA(cudaMalloc(&scratch.state, mma_state_bytes(cap_q) + 64));  // (+ 8 debug words)
+            MMA_CUDA(cudaMemsetAsync(scratch.state, 0, mma_state_bytes(cap_q) + 64, m.stream));
             scratch.state_q = cap_q;
         }
         __nv_bfloat16* qb = reinterpret_cast<__nv_bfloat16*>(scratch.p);
@@ -998,6 +187,7 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
         a.k = m.k;
         a.row_offset = m.row_offset;
         a.row_stride = m.row_stride ? m.row_stride : 1u;
+        a.scale_bounded = m.scale_bounded ? 1 : 0;
         a.n_tiles = n_tiles;
         a.q_tiles = QT;
         a.P = P;
@@ -1016,14 +206,16 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
         a.split = split ? 1 : 0;
         a.fused_tail = fused_tail ? 1 : 0;
         a.cand = lists;
-        a.cand_ld = P * m.k;
+        a.cand_ld = P * halves * m.k;
         a.cnt = cnt;
         a.done = group_done;
         a.out = m.out + static_cast<size_t>(done) * m.k;
+        static const bool debug = getenv("CODDVEC_K3_DEBUG") != nullptr;
+        a.dbg = debug ? reinterpret_cast<unsigned long long*>(scratch.state + mma_state_bytes(scratch.state_q)) : nullptr;
 
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(static_cast<unsigned>(QT * P * cg));
-        cfg.blockDim = dim3(kThreads);
+        cfg.blockDim = dim3(static_cast<unsigned>(64 + 32 * ew));
         cfg.dynamicSmemBytes = smem;
         cfg.stream = m.stream;
         cudaLaunchAttribute attr[1];
@@ -1044,6 +236,14 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
             if (launches) launches->fetch_add(1);
         }
         done += Bs;
+        if (a.dbg) {  // CODDVEC_K3_DEBUG: in-kernel timers of the fused phases (synchronises; never set in production)
+            unsigned long long w[4] = {0, 0, 0, 0};
+            MMA_CUDA(cudaStreamSynchronize(m.stream));
+            MMA_CUDA(cudaMemcpy(w, a.dbg, sizeof(w), cudaMemcpyDeviceToHost));
+            MMA_CUDA(cudaMemset(a.dbg, 0, sizeof(w)));
+            fprintf(stderr, "[k3 debug] B=%d cg=%d P=%d: prep %.1f us, publish %.1f us, merge %.1f us, max survivors/query %llu\n", Bs, cg, P,
+                    w[0] * 1e-3, w[1] * 1e-3, w[2] * 1e-3, w[3]);
+        }
     }
     return 0;
 }

@@ -27,6 +27,7 @@ struct MmaArgs {
     uint32_t row_offset;
     uint32_t row_stride;    // global row = row_offset + local row * row_stride (0 / 1 = dense)
     int precision;          // CV_PRECISION_*
+    bool scale_bounded;     // every row scale is 0, NaN or within 2^-7 of 1
     const float* q;         // [B][D] fp32 raw (device)
     int B, k;
     uint64_t* out;          // [B][k]

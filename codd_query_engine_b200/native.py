@@ -134,12 +134,18 @@ def load_library() -> ctypes.CDLL:
                                                     u64, vp, vp]),
         "cv_query_exchange": (ctypes.c_int, [vp, vp, ctypes.POINTER(_QueryParams), ctypes.POINTER(_PeerExchange),
                                              u64, vp, vp, vp]),
+        "cv_group_create": (ctypes.c_int, [ctypes.POINTER(vp), i32, i32, i32, ctypes.POINTER(vp)]),
+        "cv_group_destroy": (None, [vp]),
+        "cv_group_query": (ctypes.c_int, [vp, vp, ctypes.POINTER(_QueryParams), ctypes.POINTER(vp), vp, vp, vp]),
         "cv_merge_keys_device": (ctypes.c_int, [i32, vp, i32, i32, i32, i32, vp, vp]),
         "cv_decode_keys": (None, [vp, i64, vp, vp]),
         "cv_encode_key": (u64, [ctypes.c_float, u32]),
         "cv_get_rows": (ctypes.c_int, [vp, vp, i64, vp, vp, vp, vp]),
         "cv_load_rows": (ctypes.c_int, [vp, vp, vp, vp, vp, i64, vp]),
+        "cv_delete_rows": (ctypes.c_int, [vp, vp, i64]),
+        "cv_set_codes": (ctypes.c_int, [vp, vp, vp, vp, i64]),
         "cv_debug_mma_scores": (ctypes.c_int, [vp, vp, i32, i32, i32, vp]),
+        "cv_device_count": (i32, []),
         "cv_count": (i64, [vp]),
         "cv_dim": (i32, [vp]),
         "cv_set_profiling": (ctypes.c_int, [vp, i32]),
@@ -158,8 +164,9 @@ def load_library() -> ctypes.CDLL:
 
 EXPORTED_SYMBOLS = (
     "cv_create", "cv_destroy", "cv_upsert", "cv_upsert_device", "cv_query", "cv_query_device",
-    "cv_peer_exchange_bytes", "cv_query_device_exchange", "cv_query_exchange", "cv_merge_keys_device", "cv_decode_keys",
-    "cv_encode_key", "cv_get_rows", "cv_load_rows", "cv_debug_mma_scores", "cv_count", "cv_dim",
+    "cv_peer_exchange_bytes", "cv_query_device_exchange", "cv_query_exchange", "cv_group_create", "cv_group_destroy",
+    "cv_group_query", "cv_merge_keys_device", "cv_decode_keys",
+    "cv_encode_key", "cv_get_rows", "cv_load_rows", "cv_delete_rows", "cv_set_codes", "cv_debug_mma_scores", "cv_device_count", "cv_count", "cv_dim",
     "cv_set_profiling", "cv_stats", "cv_synchronize", "cv_last_error", "cv_version",
 )
 
@@ -191,6 +198,11 @@ def decode_keys(keys: np.ndarray):
 
 def encode_key(score: float, row: int) -> int:
     return int(load_library().cv_encode_key(float(score), int(row)))
+
+
+def device_count() -> int:
+    """CUDA devices this process can see (0 without a driver / GPU)."""
+    return int(load_library().cv_device_count())
 
 
 def peer_exchange_bytes(world: int, max_queries: int, max_k: int) -> int:
@@ -298,9 +310,21 @@ class NativeIndex:
         _check(self._lib.cv_load_rows(self._h, _ptr(vec), _ptr(sc), _ptr(ns), _ptr(lb), n, _ptr(out)))
         return out
 
+    def delete_rows(self, rows) -> None:
+        """Mark local rows dead: no query returns them until an upsert reuses the slot (no per-query mask needed)."""
+        r = np.ascontiguousarray(rows, dtype=np.int64)
+        _check(self._lib.cv_delete_rows(self._h, _ptr(r), r.shape[0]))
+
+    def set_codes(self, rows, ns_codes=None, label_codes=None) -> None:
+        """Rewrite the namespace / label predicate codes of local rows in place (metadata-only updates)."""
+        r = np.ascontiguousarray(rows, dtype=np.int64)
+        ns = None if ns_codes is None else np.ascontiguousarray(ns_codes, dtype=np.uint32)
+        lb = None if label_codes is None else np.ascontiguousarray(label_codes, dtype=np.uint32)
+        _check(self._lib.cv_set_codes(self._h, _ptr(r), _ptr(ns), _ptr(lb), r.shape[0]))
+
     # -- K2 / K3 / K4
     def query(self, queries: np.ndarray, k: int, ns_code: int = ANY, label_code: int = ANY, mask=None,
-              path: int = PATH_AUTO, precision: int = PRECISION_AUTO):
+              path: int = PATH_AUTO, precision: int = PRECISION_AUTO, mask_bits=None):
         """Host API.  Returns (scores [B][k] fp32 desc, rows [B][k] int64 global (-1 pad), counts [B])."""
         q = np.ascontiguousarray(queries, dtype=np.float32)
         if q.ndim == 1:
@@ -309,6 +333,10 @@ class NativeIndex:
             raise ValueError(f"queries must be [B][{self.dim}], got {q.shape}")
         B = q.shape[0]
         m = None
+        if mask is None and mask_bits is not None:  # the bool array a mask would be packed from (see where.pack_mask)
+            bits = np.asarray(mask_bits, dtype=bool)
+            pad = (-bits.shape[0]) % 32
+            mask = np.packbits(np.concatenate([bits, np.zeros(pad, dtype=bool)]) if pad else bits, bitorder="little").view(np.uint32)
         if mask is not None:
             m = np.ascontiguousarray(mask, dtype=np.uint32)
             need = (len(self) + 31) // 32
@@ -386,3 +414,194 @@ class NativeIndex:
 
     def synchronize(self) -> None:
         _check(self._lib.cv_synchronize(self._h))
+
+
+class StripedIndex:
+    """One collection striped over G devices of THIS process (include/coddvec.h: cv_group).
+
+    Global row r lives on shard r % G at local row r // G: appends (global rows are handed out densely, in order)
+    stay balanced to within one row, and result keys carry the global row, so ties break exactly as on one GPU.
+    The interface is NativeIndex's -- `Collection` uses either without knowing which -- and a query is ONE C call
+    (cv_group_query) that puts the batch in flight on every device, lets the kernels exchange their per-GPU top-k
+    over NVLink peer stores, and returns shard 0's merged answer.  This is how the reference's single-process
+    service (codd_lib/codd_lib/client/provider/promql_module.py:59-67 builds one client for the whole process)
+    gets more than one GPU.
+    """
+
+    def __init__(self, dim: int, metric: int = METRIC_COSINE, devices=(0, 1), capacity_rows: int = 0, max_rows: int = 0,
+                 max_queries: int = 1024, max_k: int = MAX_K):
+        devices = [int(d) for d in devices]
+        if len(devices) < 2:
+            raise ValueError("a striped index needs at least two shards")
+        self._lib = load_library()
+        self.dim, self.metric, self.devices = int(dim), int(metric), devices
+        G = self.G = len(devices)
+        per = lambda n: -(-int(n) // G) if n else 0  # noqa: E731
+        self.shards = [NativeIndex(dim, metric=metric, device=d, capacity_rows=per(capacity_rows), max_rows=per(max_rows),
+                                   row_offset=g, row_stride=G) for g, d in enumerate(devices)]
+        handles = (ctypes.c_void_p * G)(*[sh._h for sh in self.shards])
+        self._g = ctypes.c_void_p()
+        try:
+            _check(self._lib.cv_group_create(handles, G, int(max_queries), int(max_k), ctypes.byref(self._g)))
+        except Exception:
+            for sh in self.shards:
+                sh.close()
+            raise
+        self.max_queries, self.max_k = int(max_queries), int(max_k)
+        self.device = devices[0]
+        self.row_offset, self.row_stride = 0, 1  # (as seen from outside: dense global rows)
+
+    # -- lifecycle
+    def close(self) -> None:
+        if getattr(self, "_g", None) is not None and self._g:
+            self._lib.cv_group_destroy(self._g)
+            self._g = ctypes.c_void_p()
+            for sh in self.shards:
+                sh.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self) -> int:
+        return sum(len(sh) for sh in self.shards)
+
+    count = __len__
+
+    # -- K1
+    def upsert(self, embeddings: np.ndarray, rows=None, ns_codes=None, label_codes=None) -> np.ndarray:
+        emb = np.ascontiguousarray(embeddings, dtype=np.float32)
+        if emb.ndim != 2 or emb.shape[1] != self.dim:
+            raise ValueError(f"embeddings must be [n][{self.dim}], got {emb.shape}")
+        n = emb.shape[0]
+        if not np.isfinite(emb).all():  # checked for the WHOLE batch before any shard is touched
+            raise ValueError("coddvec: embeddings contain NaN/Inf; nothing was committed")
+        total = len(self)
+        want = np.full(n, -1, dtype=np.int64) if rows is None else np.ascontiguousarray(rows, dtype=np.int64).copy()
+        if want.shape != (n,):
+            raise ValueError(f"rows must have shape ({n},)")
+        if (want >= total).any():
+            raise ValueError(f"coddvec: row {int(want.max())} is not committed (count = {total})")
+        fresh = want < 0
+        glob = want.copy()
+        glob[fresh] = total + np.arange(int(fresh.sum()), dtype=np.int64)  # dense global rows, in batch order
+        ns = None if ns_codes is None else np.ascontiguousarray(ns_codes, dtype=np.uint32)
+        lb = None if label_codes is None else np.ascontiguousarray(label_codes, dtype=np.uint32)
+        for g, sh in enumerate(self.shards):
+            pos = np.nonzero(glob % self.G == g)[0]
+            if pos.size == 0:
+                continue
+            local = np.where(fresh[pos], -1, glob[pos] // self.G)
+            got = sh.upsert(emb[pos], rows=local, ns_codes=None if ns is None else ns[pos],
+                            label_codes=None if lb is None else lb[pos])
+            if not np.array_equal(got * self.G + g, glob[pos]):
+                raise NativeError(CV_ERR_CUDA, "striped index lost its row numbering (a shard was written behind its back)")
+        return glob
+
+    def load_rows(self, stored_bf16: np.ndarray, scale: np.ndarray, ns_codes=None, label_codes=None) -> np.ndarray:
+        vec = np.ascontiguousarray(stored_bf16, dtype=np.uint16)
+        n = vec.shape[0]
+        glob = len(self) + np.arange(n, dtype=np.int64)
+        sc = np.ascontiguousarray(scale, dtype=np.float32)
+        for g, sh in enumerate(self.shards):
+            pos = np.nonzero(glob % self.G == g)[0]
+            if pos.size:
+                sh.load_rows(vec[pos], sc[pos], None if ns_codes is None else np.asarray(ns_codes)[pos],
+                             None if label_codes is None else np.asarray(label_codes)[pos])
+        return glob
+
+    # -- K2 / K3 + fused exchange
+    def query(self, queries: np.ndarray, k: int, ns_code: int = ANY, label_code: int = ANY, mask=None,
+              path: int = PATH_AUTO, precision: int = PRECISION_AUTO, mask_bits=None):
+        """Same contract as NativeIndex.query; `mask` is over GLOBAL rows (u32 words), or pass the bool array it was
+        packed from as `mask_bits` to skip the unpack."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise ValueError(f"queries must be [B][{self.dim}], got {q.shape}")
+        B = q.shape[0]
+        total = len(self)
+        masks = None
+        keep = []
+        if mask is not None or mask_bits is not None:
+            if mask_bits is None:
+                words = np.ascontiguousarray(mask, dtype=np.uint32)
+                if words.shape[0] < (total + 31) // 32:
+                    raise ValueError(f"mask needs {(total + 31) // 32} uint32 words, got shape {words.shape}")
+                mask_bits = np.unpackbits(words.view(np.uint8), bitorder="little")[:total].astype(bool)
+            bits = np.asarray(mask_bits, dtype=bool)[:total]
+            masks = (ctypes.c_void_p * self.G)()
+            for g in range(self.G):
+                part = bits[g::self.G]
+                pad = (-part.shape[0]) % 32
+                if pad:
+                    part = np.concatenate([part, np.zeros(pad, dtype=bool)])
+                w = np.packbits(part, bitorder="little").view(np.uint32) if part.size else np.zeros(1, np.uint32)
+                keep.append(w)
+                masks[g] = w.ctypes.data
+        scores = np.empty((B, int(k)), dtype=np.float32)
+        rows = np.empty((B, int(k)), dtype=np.int64)
+        counts = np.empty(B, dtype=np.int32)
+        if B > self.max_queries:  # larger than the exchange buffers: slices
+            for lo in range(0, B, self.max_queries):
+                hi = min(B, lo + self.max_queries)
+                scores[lo:hi], rows[lo:hi], counts[lo:hi] = self.query(q[lo:hi], k, ns_code, label_code, path=path,
+                                                                       precision=precision, mask_bits=mask_bits)
+            return scores, rows, counts
+        p = _QueryParams(B, int(k), int(ns_code), int(label_code), None, int(path), int(precision))
+        _check(self._lib.cv_group_query(self._g, _ptr(q), ctypes.byref(p), masks, _ptr(scores), _ptr(rows), _ptr(counts)))
+        return scores, rows, counts
+
+    def delete_rows(self, rows) -> None:
+        r = np.ascontiguousarray(rows, dtype=np.int64)
+        for g, sh in enumerate(self.shards):
+            pos = np.nonzero(r % self.G == g)[0]
+            if pos.size:
+                sh.delete_rows(r[pos] // self.G)
+
+    def set_codes(self, rows, ns_codes=None, label_codes=None) -> None:
+        r = np.ascontiguousarray(rows, dtype=np.int64)
+        for g, sh in enumerate(self.shards):
+            pos = np.nonzero(r % self.G == g)[0]
+            if pos.size:
+                sh.set_codes(r[pos] // self.G, None if ns_codes is None else np.asarray(ns_codes)[pos],
+                             None if label_codes is None else np.asarray(label_codes)[pos])
+
+    # -- readback / bookkeeping
+    def get_rows(self, rows, want_vectors: bool = True):
+        r = np.ascontiguousarray(rows, dtype=np.int64)
+        n = r.shape[0]
+        vec = np.empty((n, self.dim), dtype=np.uint16) if want_vectors else None
+        scale = np.empty(n, dtype=np.float32)
+        ns = np.empty(n, dtype=np.uint32)
+        lb = np.empty(n, dtype=np.uint32)
+        if n and (r.min() < 0 or r.max() >= len(self)):
+            raise ValueError(f"coddvec: row out of range [0, {len(self)})")
+        for g, sh in enumerate(self.shards):
+            pos = np.nonzero(r % self.G == g)[0]
+            if pos.size == 0:
+                continue
+            v, s, a, b = sh.get_rows(r[pos] // self.G, want_vectors=want_vectors)
+            if want_vectors:
+                vec[pos] = v
+            scale[pos], ns[pos], lb[pos] = s, a, b
+        return vec, scale, ns, lb
+
+    def set_profiling(self, enabled: bool) -> None:
+        for sh in self.shards:
+            sh.set_profiling(enabled)
+
+    def stats(self) -> Stats:
+        """Shard 0's view with the additive counters summed over the shards."""
+        parts = [sh.stats() for sh in self.shards]
+        s = parts[0]
+        for f in ("rows", "capacity_rows", "kernel_launches", "upserted_rows", "last_query_bytes"):
+            setattr(s, f, sum(getattr(p, f) for p in parts))
+        return s
+
+    def synchronize(self) -> None:
+        for sh in self.shards:
+            sh.synchronize()

@@ -118,13 +118,15 @@ class ShardedIndex:
         return torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else 0
 
     def query_device(self, q: torch.Tensor, k: int, ns_code: int = native.ANY, label_code: int = native.ANY,
-                     path: int = native.PATH_AUTO) -> torch.Tensor:
+                     path: int = native.PATH_AUTO, exchange: Optional[str] = None) -> torch.Tensor:
         """q: [B][dim] fp32 on this rank's device (same values on every rank).  Returns the merged
-        [B][k] int64 key tensor (u64 bit patterns) on every rank.  Asynchronous on the current stream."""
+        [B][k] int64 key tensor (u64 bit patterns) on every rank.  Asynchronous on the current stream.
+        exchange="nccl" forces the all-gather + K4 exchange for this call (every rank must pass the same value)."""
         B = q.shape[0]
         local, gathered, merged = self._buffers(B, k)
         stream = self._stream()
-        if self.world > 1 and self._px is not None and B <= self._px_caps[0] and k <= self._px_caps[1]:
+        fused = exchange != "nccl"
+        if fused and self.world > 1 and self._px is not None and B <= self._px_caps[0] and k <= self._px_caps[1]:
             self._seq += 1  # fused: scan + NVLink peer stores + flag wait + merge, no collective launch
             self.local.query_device_exchange(q.data_ptr(), B, k, merged.data_ptr(), self._px, self._seq, ns_code=ns_code,
                                              label_code=label_code, path=path, stream=stream)

@@ -95,8 +95,22 @@ def _as_equality(clause: dict):
 class CompiledWhere:
     ns_code: int = ANY
     label_code: int = ANY
-    mask_words: Optional[np.ndarray] = None  # uint32 [ceil(n/32)]
+    mask_bits: Optional[np.ndarray] = None   # bool [n], or None = every row
     empty: bool = False                      # provably matches nothing
+    _words: Optional[np.ndarray] = None
+
+    @property
+    def mask_words(self) -> Optional[np.ndarray]:
+        """The bitmask the kernels take: uint32 [ceil(n/32)], packed on first use."""
+        if self.mask_bits is None:
+            return None
+        if self._words is None:
+            self._words = pack_mask(self.mask_bits)
+        return self._words
+
+    @property
+    def eligible(self) -> Optional[int]:
+        return None if self.mask_bits is None else int(np.count_nonzero(self.mask_bits))
 
 
 def pack_mask(bits: np.ndarray) -> np.ndarray:
@@ -108,12 +122,94 @@ def pack_mask(bits: np.ndarray) -> np.ndarray:
     return np.packbits(bits, bitorder="little").view(np.uint32)
 
 
+_MISSING = object()
+
+
+class MetadataColumns:
+    """Dictionary-encoded metadata columns, one per field a `where` clause has touched, kept in step with the rows.
+
+    A residual clause (anything but the fused namespace / label equalities) used to be evaluated by a Python loop
+    over every row per query.  Here a field's values are coded once (code 0 = the row has no such key), a clause
+    is evaluated once per DISTINCT value with the very comparison `evaluate` uses, and the per-row answer is one
+    numpy gather `truth[codes]` -- identical results, milliseconds at a million rows.
+    """
+
+    def __init__(self):
+        self._cols: dict[str, tuple[np.ndarray, list, dict]] = {}  # field -> (codes int32 [cap], values, code_of)
+
+    def _code(self, col, value) -> int:
+        codes, values, code_of = col
+        key = (type(value).__name__, value)  # 1, 1.0 and True stay distinct values, as in `evaluate`
+        c = code_of.get(key)
+        if c is None:
+            c = len(values)
+            values.append(value)
+            code_of[key] = c
+        return c
+
+    def column(self, field: str, metadatas: Sequence[Optional[dict]]):
+        col = self._cols.get(field)
+        n = len(metadatas)
+        if col is None:
+            col = (np.zeros(max(n, 16), dtype=np.int32), [_MISSING], {})
+            for r, md in enumerate(metadatas):
+                if md is not None and field in md:
+                    col[0][r] = self._code(col, md[field])
+            self._cols[field] = col
+        elif col[0].shape[0] < n:  # rows appended since (set_row grows it too; this covers direct table edits)
+            grown = np.zeros(max(n, 2 * col[0].shape[0]), dtype=np.int32)
+            grown[: col[0].shape[0]] = col[0]
+            col = (grown, col[1], col[2])
+            self._cols[field] = col
+        return col
+
+    def set_row(self, row: int, metadata: Optional[dict]) -> None:
+        """Row `row` now carries `metadata` (None = deleted): update every tracked column."""
+        for field, col in list(self._cols.items()):
+            if col[0].shape[0] <= row:
+                grown = np.zeros(max(row + 1, 2 * col[0].shape[0]), dtype=np.int32)
+                grown[: col[0].shape[0]] = col[0]
+                col = (grown, col[1], col[2])
+                self._cols[field] = col
+            col[0][row] = self._code(col, metadata[field]) if metadata is not None and field in metadata else 0
+
+    def evaluate_rows(self, where: dict, metadatas: Sequence[Optional[dict]]) -> np.ndarray:
+        """bool [n]: `evaluate(where, metadatas[r])` for every row, vectorised."""
+        n = len(metadatas)
+        (key, val), = where.items()
+        if key == "$and":
+            out = np.ones(n, dtype=bool)
+            for sub in val:
+                out &= self.evaluate_rows(sub, metadatas)
+            return out
+        if key == "$or":
+            out = np.zeros(n, dtype=bool)
+            for sub in val:
+                out |= self.evaluate_rows(sub, metadatas)
+            return out
+        if isinstance(val, dict):
+            (op, operand), = val.items()
+        else:
+            op, operand = "$eq", val
+        codes, values, _ = self.column(key, metadatas)
+        truth = np.zeros(len(values), dtype=bool)
+        truth[0] = op in ("$ne", "$nin")  # the row has no such key
+        for c in range(1, len(values)):
+            try:
+                truth[c] = bool(_CMP[op](values[c], operand))
+            except TypeError:
+                truth[c] = False
+        return truth[codes[:n]]
+
+
 def compile_where(where: Optional[dict], metadatas: Sequence[Optional[dict]], ns_codes: dict, label_field: str,
-                  label_codes: dict, alive: Optional[np.ndarray] = None) -> CompiledWhere:
+                  label_codes: dict, alive: Optional[np.ndarray] = None,
+                  columns: Optional[MetadataColumns] = None) -> CompiledWhere:
     """Split `where` into fused column predicates + a host-evaluated bitmask.
 
     metadatas: per-row metadata dicts (row order).  ns_codes / label_codes: value -> u32 code of the
-    device columns.  alive: optional bool [n] of rows that exist (tombstones cleared).
+    device columns.  alive: optional bool [n] of rows that exist (tombstones cleared).  columns: the collection's
+    MetadataColumns (vectorised residual clauses); without it the clauses are evaluated row by row.
     """
     out = CompiledWhere()
     n = len(metadatas)
@@ -140,12 +236,17 @@ def compile_where(where: Optional[dict], metadatas: Sequence[Optional[dict]], ns
                 residual.append(cl)
     bits = None
     if residual:
-        bits = np.fromiter((all(evaluate(cl, md) for cl in residual) for md in metadatas), dtype=bool, count=n)
+        if columns is not None:
+            bits = np.ones(n, dtype=bool)
+            for cl in residual:
+                bits &= columns.evaluate_rows(cl, metadatas)
+        else:
+            bits = np.fromiter((all(evaluate(cl, md) for cl in residual) for md in metadatas), dtype=bool, count=n)
     if alive is not None and not alive.all():
         bits = alive.copy() if bits is None else (bits & alive)
     if bits is not None:
         if not bits.any():
             out.empty = True
             return out
-        out.mask_words = pack_mask(bits)
+        out.mask_bits = bits
     return out

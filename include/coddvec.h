@@ -153,6 +153,20 @@ int cv_query_device_exchange(cv_index* idx, const float* d_q, const cv_query_par
 int cv_query_exchange(cv_index* idx, const float* q, const cv_query_params* p, const cv_peer_exchange* px,
                       uint64_t seq, float* out_scores, int64_t* out_rows, int32_t* out_counts);
 
+/* One PROCESS serving G GPUs (the reference builds one client in one process: codd_lib/codd_lib/client/provider/
+ * promql_module.py:59-67): a collection striped over G devices -- shard g is a cv_index created with row_stride = G
+ * and row_offset = g, i.e. global row r lives on shard r % G at local row r / G, so appends stay balanced and ties
+ * still break by global row id.  cv_group_create allocates one exchange buffer per device and maps it into the
+ * others (cudaDeviceEnablePeerAccess); cv_group_query is cv_query for the whole collection: it puts the batch in
+ * flight on every device (same kernels, fused NVLink exchange as in cv_query_exchange), waits for shard 0's merged
+ * result and returns it.  masks: NULL, or one bitmask per shard over that shard's LOCAL rows (entries may be NULL).
+ * p->mask is ignored.  Calls on one group are serialised.  The group does not own its shards. */
+typedef struct cv_group cv_group;
+int cv_group_create(cv_index* const* shards, int32_t n_shards, int32_t max_queries, int32_t max_k, cv_group** out);
+void cv_group_destroy(cv_group* grp);
+int cv_group_query(cv_group* grp, const float* q, const cv_query_params* p, const uint32_t* const* masks,
+                   float* out_scores, int64_t* out_rows, int32_t* out_counts);
+
 /* K4: merge G per-shard key lists [G][B][k_in] (device) into [B][k_out] (device) on `stream`
  * of `device`.  Used after the NCCL all-gather of per-GPU top-k. */
 int cv_merge_keys_device(int32_t device, const uint64_t* d_keys_in, int32_t G, int32_t B, int32_t k_in,
@@ -168,6 +182,14 @@ uint64_t cv_encode_key(float score, uint32_t global_row);
 int cv_get_rows(cv_index* idx, const int64_t* rows, int64_t n, uint16_t* out_bf16, float* out_scale,
                 uint32_t* out_ns, uint32_t* out_label);
 
+/* Collection.delete (chromadb API; the reference's store never deletes, the indexer's re-runs upsert): mark local
+ * rows dead.  A dead row keeps its slot -- rows stay dense -- but no query returns it (its scale becomes NaN, which
+ * every kernel treats as "not eligible"), so deletes cost nothing per query; cv_upsert into the slot revives it. */
+int cv_delete_rows(cv_index* idx, const int64_t* rows, int64_t n);
+/* Collection.update(metadatas=...) that changes a row's namespace / label: rewrite the predicate codes of local rows
+ * in place (either array may be NULL = leave that column). */
+int cv_set_codes(cv_index* idx, const int64_t* rows, const uint32_t* ns_codes, const uint32_t* label_codes, int64_t n);
+
 /* Append n rows verbatim -- bf16 bit patterns [n][dim], scale [n], codes [n] (NULL = 0), all host memory,
  * exactly what cv_get_rows returned -- without re-normalising: restores a snapshot (the role Chroma's
  * on-disk volume plays for the reference, docker-compose.yml:8-9).  out_rows as for cv_upsert. */
@@ -179,6 +201,7 @@ int cv_load_rows(cv_index* idx, const uint16_t* bf16, const float* scale, const 
  * path: CV_PATH_MMA, CV_PATH_MMA_1CTA or CV_PATH_MMA_2CTA; precision: CV_PRECISION_*. */
 int cv_debug_mma_scores(cv_index* idx, const float* q, int32_t B, int32_t path, int32_t precision, float* out_scores);
 
+int32_t cv_device_count(void); /* CUDA devices visible to this process (0 = none: every compute call will fail) */
 int64_t cv_count(const cv_index* idx);
 int32_t cv_dim(const cv_index* idx);
 int cv_set_profiling(cv_index* idx, int32_t enabled);

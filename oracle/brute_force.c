@@ -146,6 +146,7 @@ int32_t cvo_query(const uint16_t* stored, const float* scale, int64_t n, int32_t
             if (label_code != CVO_ANY && label[i] != label_code) continue;
             const uint16_t* e = stored + i * (int64_t)D;
             float sc = scale[i];
+            if (sc != sc) continue; /* scale = NaN marks a deleted row (cv_delete_rows) */
             uint32_t row = (uint32_t)(row_offset + i);
             for (int b = 0; b < B; ++b) {
                 float s = dot_bf16(e, qhat + (int64_t)b * D, D) * sc;

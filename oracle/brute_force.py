@@ -209,6 +209,7 @@ def query(stored_bits, scale, q, k, metric=METRIC_COSINE, mask_words=None, ns=No
     qhat = normalise_query(q, metric)
     B = qhat.shape[0]
     elig = eligible_rows(n, mask_words, ns, ns_code, label, label_code)
+    elig = elig & ~np.isnan(np.asarray(scale, dtype=np.float32))  # scale = NaN marks a deleted row (cv_delete_rows)
     best = np.zeros((B, k), dtype=np.uint64)
     for lo in range(0, n, chunk):
         hi = min(n, lo + chunk)

@@ -10,7 +10,7 @@ from oracle import brute_force as bf
 
 
 class OracleIndex:
-    def __init__(self, dim, metric=bf.METRIC_COSINE, device=0, capacity_rows=0, max_rows=0, row_offset=0):
+    def __init__(self, dim, metric=bf.METRIC_COSINE, device=0, capacity_rows=0, max_rows=0, row_offset=0, row_stride=1):
         self.dim, self.metric, self.device, self.row_offset = int(dim), int(metric), int(device), int(row_offset)
         self._stored = np.zeros((0, dim), np.uint16)
         self._scale = np.zeros(0, np.float32)
@@ -56,7 +56,21 @@ class OracleIndex:
             out[i] = r
         return out
 
-    def query(self, queries, k, ns_code=bf.ANY_CODE, label_code=bf.ANY_CODE, mask=None, path=0):
+    def delete_rows(self, rows):
+        self._scale[np.asarray(rows, np.int64)] = np.nan
+
+    def set_codes(self, rows, ns_codes=None, label_codes=None):
+        r = np.asarray(rows, np.int64)
+        if ns_codes is not None:
+            self._ns[r] = np.asarray(ns_codes, np.uint32)
+        if label_codes is not None:
+            self._label[r] = np.asarray(label_codes, np.uint32)
+
+    def query(self, queries, k, ns_code=bf.ANY_CODE, label_code=bf.ANY_CODE, mask=None, path=0, precision=0, mask_bits=None):
+        if mask is None and mask_bits is not None:
+            bits = np.asarray(mask_bits, dtype=bool)
+            pad = (-bits.shape[0]) % 32
+            mask = np.packbits(np.concatenate([bits, np.zeros(pad, dtype=bool)]) if pad else bits, bitorder="little").view(np.uint32)
         q = np.ascontiguousarray(queries, dtype=np.float32)
         if q.ndim == 1:
             q = q[None, :]

@@ -162,14 +162,14 @@ def test_scan_predicates(native):
     check_topk(s, r, c, full, bits, k, tol=2e-6)
     s, r, c = idx.query(q, k, mask=words, ns_code=5, path=native.PATH_SCAN)
     check_topk(s, r, c, full, bits & (ns == 5), k, tol=2e-6)
+    # oracle's own predicate path agrees (counts, scores, and rows wherever scores are not within rounding of a tie)
+    es, er, ec = bf.query(stored, scale, q, k, mask_words=words, ns=ns, ns_code=5)
+    assert np.array_equal(ec, c) and np.abs(es - s).max() <= 2e-6
+    differ = er != r
+    assert not differ.any() or (np.abs(np.diff(es, axis=1)).min(axis=1)[differ.any(axis=1)] <= 4e-6).all()
     # nothing eligible
     s, r, c = idx.query(q, k, ns_code=77, path=native.PATH_SCAN)
     assert (c == 0).all() and (r == -1).all()
-    # oracle's own predicate path agrees
-    es, er, ec = bf.query(stored, scale, q, k, mask_words=words, ns=ns, ns_code=5)
-    assert np.array_equal(ec, c) and np.abs(es - s).max() <= 2e-6
-    for b in range(q.shape[0]):
-        assert set(er[b, :ec[b]].tolist()) == set(r[b, :c[b]].tolist()) or np.abs(es[b] - s[b]).max() <= 2e-6
     idx.close()
 
 
