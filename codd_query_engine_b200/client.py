@@ -528,28 +528,42 @@ class Collection:
     # cv_get_rows) + one JSON line per row (id, metadata, document).  This replaces the Chroma
     # server's docker volume (docker-compose.yml:8-9) -- SURVEY.md section 8(f) rank 3.
     def save(self, directory: str) -> None:
+        """Write the snapshot into a fresh sibling directory and rename it into place: a crash at any point leaves
+        either the previous snapshot or the new one, never a mix (the data files of one snapshot are only ever
+        seen together with the meta.json that describes them)."""
+        directory = os.path.abspath(directory)
+        parent = os.path.dirname(directory)
+        os.makedirs(parent, exist_ok=True)
+        tmp = f"{directory}.tmp-{os.getpid()}-{uuid.uuid4().hex[:8]}"
+        os.makedirs(tmp)
         with self._lock:
-            os.makedirs(directory, exist_ok=True)
             n = len(self._ids)
+            dim = None if self._index is None else self._index.dim
             meta = {"format": 1, "name": self.name, "metadata": self.metadata, "metric": self._metric,
-                    "label_field": self._label_field, "rows": n,
-                    "dim": None if self._index is None else self._index.dim,
+                    "label_field": self._label_field, "rows": n, "dim": dim,
                     "ns_codes": list(self._ns_codes.items()), "label_codes": list(self._label_codes.items()),
                     "free_rows": list(self._free_rows)}
             if self._index is not None and n:
                 vec, scale, ns, lb = self._index.get_rows(np.arange(n, dtype=np.int64))
-                vec.tofile(os.path.join(directory, "rows.bf16"))
-                scale.tofile(os.path.join(directory, "scale.f32"))
-                ns.tofile(os.path.join(directory, "ns.u32"))
-                lb.tofile(os.path.join(directory, "label.u32"))
-            with open(os.path.join(directory, "records.jsonl"), "w", encoding="utf-8") as f:
+                vec.tofile(os.path.join(tmp, "rows.bf16"))
+                scale.tofile(os.path.join(tmp, "scale.f32"))
+                ns.tofile(os.path.join(tmp, "ns.u32"))
+                lb.tofile(os.path.join(tmp, "label.u32"))
+            with open(os.path.join(tmp, "records.jsonl"), "w", encoding="utf-8") as f:
                 for r in range(n):
                     f.write(json.dumps({"id": self._ids[r], "metadata": self._metadatas[r], "document": self._documents[r]},
                                        ensure_ascii=False) + "\n")
-            tmp = os.path.join(directory, "meta.json.tmp")
-            with open(tmp, "w", encoding="utf-8") as f:
-                json.dump(meta, f, ensure_ascii=False)
-            os.replace(tmp, os.path.join(directory, "meta.json"))  # meta.json last: its presence marks a complete snapshot
+        with open(os.path.join(tmp, "meta.json"), "w", encoding="utf-8") as f:
+            json.dump(meta, f, ensure_ascii=False)
+        old = None
+        if os.path.exists(directory):
+            old = f"{directory}.old-{uuid.uuid4().hex[:8]}"
+            os.replace(directory, old)
+        os.replace(tmp, directory)
+        if old is not None:
+            import shutil
+
+            shutil.rmtree(old, ignore_errors=True)
 
     @classmethod
     def load(cls, directory: str, embedding_function=None, device: int = 0) -> "Collection":
@@ -562,6 +576,11 @@ class Collection:
         coll._ns_codes = {k: v for k, v in meta["ns_codes"]}
         coll._label_codes = {k: v for k, v in meta["label_codes"]}
         n, dim = int(meta["rows"]), meta["dim"]
+        if dim is not None and n:  # sizes first: a truncated file must not be loaded as a shorter corpus
+            for fname, width in (("rows.bf16", 2 * int(dim)), ("scale.f32", 4), ("ns.u32", 4), ("label.u32", 4)):
+                path = os.path.join(directory, fname)
+                if not os.path.isfile(path) or os.path.getsize(path) != n * width:
+                    raise ValueError(f"snapshot {directory} is corrupt: {fname} should hold {n} rows of {width} bytes")
         with open(os.path.join(directory, "records.jsonl"), encoding="utf-8") as f:
             for line in f:
                 rec = json.loads(line)
@@ -571,6 +590,7 @@ class Collection:
         if len(coll._ids) != n:
             raise ValueError(f"snapshot {directory} is truncated: {len(coll._ids)} records for {n} rows")
         coll._alive = np.array([i is not None for i in coll._ids], dtype=bool)
+        coll._generation += 1
         for r, doc_id in enumerate(coll._ids):
             if doc_id is not None:
                 coll._ns_count(coll._metadatas[r], +1)
@@ -641,7 +661,12 @@ class Client:
     # ---- snapshots (PersistentClient): <path>/<collection>/{meta.json, rows.bf16, ...}
     @staticmethod
     def _dir_name(collection_name: str) -> str:
-        return re.sub(r"[^A-Za-z0-9._-]", "_", collection_name)
+        safe = re.sub(r"[^A-Za-z0-9._-]", "_", collection_name)
+        if safe != collection_name:  # 'a/b' and 'a_b' must not share a directory
+            import hashlib
+
+            safe += "-" + hashlib.sha1(collection_name.encode("utf-8")).hexdigest()[:10]
+        return safe
 
     def _load_snapshots(self) -> None:
         if not os.path.isdir(self._path):
@@ -649,7 +674,7 @@ class Client:
         with self._reg.lock:
             for entry in sorted(os.listdir(self._path)):
                 d = os.path.join(self._path, entry)
-                if not os.path.isfile(os.path.join(d, "meta.json")):
+                if not os.path.isfile(os.path.join(d, "meta.json")) or ".tmp-" in entry or ".old-" in entry:
                     continue
                 with open(os.path.join(d, "meta.json"), encoding="utf-8") as f:
                     name = json.load(f)["name"]
@@ -663,8 +688,18 @@ class Client:
             raise ValueError("persist() needs a path (or a client made with PersistentClient(path))")
         with self._reg.lock:
             colls = list(self._reg.collections.values())
+        keep = set()
         for coll in colls:
+            keep.add(self._dir_name(coll.name))
             coll.save(os.path.join(root, self._dir_name(coll.name)))
+        # collections deleted since the last persist() must not come back on the next load
+        if os.path.isdir(root):
+            import shutil
+
+            for entry in os.listdir(root):
+                d = os.path.join(root, entry)
+                if entry not in keep and os.path.isfile(os.path.join(d, "meta.json")):
+                    shutil.rmtree(d, ignore_errors=True)
         return root
 
     def heartbeat(self) -> int:
@@ -735,7 +770,11 @@ def EphemeralClient(**kwargs) -> Client:  # noqa: N802 - chromadb's factory name
 
 def HttpClient(host: str = "localhost", port: int = 8000, **kwargs) -> Client:  # noqa: N802
     """In-process stand-in for ``chromadb.HttpClient(host, port)`` (codd_lib/.../promql_module.py:59-62,
-    codd_jobs/metrics_semantic_indexer_main.py:209-212): the "server" is this process's GPU."""
+    codd_jobs/metrics_semantic_indexer_main.py:209-212): the "server" is this process's GPU.
+
+    The stand-in is PER PROCESS: an indexer job and a service that ran against one Chroma server share data here
+    only through snapshots -- the job calls ``client.persist()`` (or sets CODDVEC_SNAPSHOT_DIR and persists at exit),
+    the service loads them when it builds its first client."""
     kwargs.pop("ssl", None)
     kwargs.pop("headers", None)
     kwargs.pop("settings", None)

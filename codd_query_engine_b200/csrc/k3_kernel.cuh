@@ -639,8 +639,11 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
         const int half = (warp - 2) >> 2;                // which alternate column chunks this thread scans (EW = 8)
         const int qlane = 32 * (warp & 3) + lane;        // TMEM lane = query within this CTA's 128
         const int qglobal = (qt * CG + static_cast<int>(rank)) * kQ + qlane;
-        const int owner = p * kHalves + half;            // this thread's slot among the lists / heads of its query
+        const int owner = half * a.P + p;                // this thread's slot among the lists / heads of its query
         const int owners = a.P * kHalves;
+        // (heads bound: a thread ranks the heads of its OWN column half only -- k distinct owners there still each
+        // hold a row at least that good, and the refresh costs what it does with four epilogue warps)
+        const uint32_t* const my_heads = a.heads + static_cast<size_t>(qglobal) * kHeadsLd + half * ((a.P + 3) / 4 * 4);
         const bool fused_tail = KREG > 0 && a.fused_tail != 0;
         uint64_t* const glist = fused_tail ? nullptr : a.lists + (static_cast<size_t>(owner) * a.Bpad + qglobal) * a.k;
         // large k (KREG == 0): the working list is in shared memory when it fits (fast warp-cooperative
@@ -709,7 +712,7 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
                 // tail publishes the keys above the bound folded in by then)
                 const bool last = tcount + 1 == my_tiles && my_tiles > 2;
                 if (tcount == next_refresh || last) {
-                    if (tcount * 8 <= my_tiles || last) fold_shared(heads_bound(head_row, owners, a.k));
+                    if (tcount * 8 <= my_tiles || last) fold_shared(heads_bound(my_heads, a.P, a.k));
                     if (tcount == next_refresh) next_refresh *= 4;
                 }
             }
@@ -777,7 +780,7 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
                                 thr = fmaxf(thr, thr_local);
                                 if (share && s > best_local) {  // publish this owner's new head for the query
                                     best_local = s;
-                                    __stcg(head_row + owner, ord_of(s));
+                                    __stcg(head_row + half * ((a.P + 3) / 4 * 4) + p, ord_of(s));
                                 }
                                 changed = true;
                             }
@@ -890,7 +893,7 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
                         // every CTA of the group is done: leave the shared state zero for the next launch
                         a.cnt[qglobal] = 0u;
                         a.gthr[qglobal] = 0u;
-                        for (int v = 0; v < (owners + 3) / 4; ++v) reinterpret_cast<uint4*>(head_row)[v] = make_uint4(0u, 0u, 0u, 0u);
+                        for (int v = 0; v < kHalves * ((a.P + 3) / 4); ++v) reinterpret_cast<uint4*>(head_row)[v] = make_uint4(0u, 0u, 0u, 0u);
                     }
                     if (et == 0) a.done[group] = 0u;
                     if (a.dbg && lane == 0) atomicMax(a.dbg + 2, global_timer_ns() - t_merge);
@@ -915,18 +918,18 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
 
 using MmaKernel = void (*)(const CUtensorMap, const CUtensorMap, const KArgs);
 
-// k <= 32 runs with 8 epilogue warps (ew = 4 selectable for A/B at k <= 16); longer register lists and the
-// shared- / global-memory lists keep 4 (register budget: 65536 / 320 threads = 204 per thread).
+// k <= 16: four or eight epilogue warps (the host picks by batch size); k <= 32: eight; longer register lists and the
+// shared- / global-memory lists keep four (register budget: 65536 / 320 threads = 204 per thread).
 template <int CG>
 inline MmaKernel pick_mma_kernel(bool dump, int k, int ew) {
     if (dump) return k_mma_topk<true, 0, CG, 4>;
-    if (k <= 10) return k_mma_topk<false, 10, CG, 8>;
+    if (k <= 10) return ew == 4 ? static_cast<MmaKernel>(k_mma_topk<false, 10, CG, 4>) : static_cast<MmaKernel>(k_mma_topk<false, 10, CG, 8>);
     if (k <= 16) return ew == 4 ? static_cast<MmaKernel>(k_mma_topk<false, 16, CG, 4>) : static_cast<MmaKernel>(k_mma_topk<false, 16, CG, 8>);
     if (k <= 32) return k_mma_topk<false, 32, CG, 8>;
     if (k <= 64) return k_mma_topk<false, 64, CG, 4>;
     return k_mma_topk<false, 0, CG, 4>;
 }
-inline int mma_kernel_epilogue_warps(bool dump, int k, int ew) { return (dump || k > 32) ? 4 : (k > 10 && k <= 16 && ew == 4 ? 4 : 8); }
+inline int mma_kernel_epilogue_warps(bool dump, int k, int ew) { return (dump || k > 32) ? 4 : (k <= 16 && ew == 4 ? 4 : 8); }
 
 MmaKernel pick_mma_kernel_cg2(bool dump, int k, int ew);  // k3_inst_cg2.cu
 

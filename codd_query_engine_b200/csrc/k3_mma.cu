@@ -114,10 +114,15 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
         return mma_fail(CV_ERR_UNSUPPORTED, "tensor-core path: query tile does not fit shared memory at dim " + std::to_string(m.Dp));
     // (CODDVEC_K3_SPLIT_LAUNCHES: bit 0 = separate query-prep launch, bit 1 = separate merge launch -- A/B switches)
     static const int split_launches = getenv("CODDVEC_K3_SPLIT_LAUNCHES") ? atoi(getenv("CODDVEC_K3_SPLIT_LAUNCHES")) : 0;
-    const bool fused_prep = q_resident && kblocks <= 8 && (split || !(split_launches & 1));  // prep_query_tile: lanes own chunks l, l + 32
+    // The query tile is built inside the kernel when that is cheap -- up to 16 queries (every CTA normalises them
+    // again, ~0.4 us per query) or short rows (the hi/lo split's second tile only exists in shared memory) --
+    // otherwise once, by k_prep_queries, and fetched by TMA: 128 live rows per CTA cost 25 us against 5 us.
+    const bool fused_prep = q_resident && kblocks <= 8 && (split || (m.B <= 16 && !(split_launches & 1)));
     const bool fused_tail = m.k <= 64 && m.dump == nullptr && !(split_launches & 2);          // register-resident lists
-    // (CODDVEC_K3_EW=4: four epilogue warps where both variants are built, k in 11..16 -- an A/B switch)
-    static const int ew_pref = getenv("CODDVEC_K3_EW") ? atoi(getenv("CODDVEC_K3_EW")) : 8;
+    // Eight epilogue warps pay when the score scan bounds the kernel (many live queries per tile); small batches are
+    // HBM-bound and run leaner with four.  (CODDVEC_K3_EW=4|8 forces one where both are built, k <= 16: A/B switch.)
+    static const int ew_env = getenv("CODDVEC_K3_EW") ? atoi(getenv("CODDVEC_K3_EW")) : 0;
+    const int ew_pref = ew_env ? ew_env : (m.B <= 32 ? 4 : 8);
     const bool dump = m.dump != nullptr;
     MmaKernel kernel = cg == 2 ? pick_mma_kernel_cg2(dump, m.k, ew_pref) : pick_mma_kernel<1>(dump, m.k, ew_pref);
     const int ew = mma_kernel_epilogue_warps(dump, m.k, ew_pref);

@@ -433,31 +433,57 @@ class StripedIndex:
         devices = [int(d) for d in devices]
         if len(devices) < 2:
             raise ValueError("a striped index needs at least two shards")
-        self._lib = load_library()
         self.dim, self.metric, self.devices = int(dim), int(metric), devices
         G = self.G = len(devices)
+        self.max_queries, self.max_k = int(max_queries), int(max_k)
         per = lambda n: -(-int(n) // G) if n else 0  # noqa: E731
-        self.shards = [NativeIndex(dim, metric=metric, device=d, capacity_rows=per(capacity_rows), max_rows=per(max_rows),
-                                   row_offset=g, row_stride=G) for g, d in enumerate(devices)]
-        handles = (ctypes.c_void_p * G)(*[sh._h for sh in self.shards])
-        self._g = ctypes.c_void_p()
+        self.shards = [self._make_shard(dim, metric=metric, device=d, capacity_rows=per(capacity_rows),
+                                        max_rows=per(max_rows), row_offset=g, row_stride=G) for g, d in enumerate(devices)]
         try:
-            _check(self._lib.cv_group_create(handles, G, int(max_queries), int(max_k), ctypes.byref(self._g)))
+            self._make_group()
         except Exception:
             for sh in self.shards:
                 sh.close()
             raise
-        self.max_queries, self.max_k = int(max_queries), int(max_k)
         self.device = devices[0]
         self.row_offset, self.row_stride = 0, 1  # (as seen from outside: dense global rows)
 
-    # -- lifecycle
-    def close(self) -> None:
+    # the three places that touch the C library (tests substitute CPU doubles for them; the product has no CPU path)
+    def _make_shard(self, dim, **kw):
+        return NativeIndex(dim, **kw)
+
+    def _make_group(self) -> None:
+        self._lib = load_library()
+        handles = (ctypes.c_void_p * self.G)(*[sh._h for sh in self.shards])
+        self._g = ctypes.c_void_p()
+        _check(self._lib.cv_group_create(handles, self.G, self.max_queries, self.max_k, ctypes.byref(self._g)))
+
+    def _group_query(self, q, k, ns_code, label_code, path, precision, shard_masks):
+        B = q.shape[0]
+        masks = None
+        if shard_masks is not None:
+            masks = (ctypes.c_void_p * self.G)()
+            for g, w in enumerate(shard_masks):
+                masks[g] = w.ctypes.data
+        scores = np.empty((B, int(k)), dtype=np.float32)
+        rows = np.empty((B, int(k)), dtype=np.int64)
+        counts = np.empty(B, dtype=np.int32)
+        p = _QueryParams(B, int(k), int(ns_code), int(label_code), None, int(path), int(precision))
+        _check(self._lib.cv_group_query(self._g, _ptr(q), ctypes.byref(p), masks, _ptr(scores), _ptr(rows), _ptr(counts)))
+        return scores, rows, counts
+
+    def _destroy_group(self) -> None:
         if getattr(self, "_g", None) is not None and self._g:
             self._lib.cv_group_destroy(self._g)
             self._g = ctypes.c_void_p()
+
+    # -- lifecycle
+    def close(self) -> None:
+        if getattr(self, "shards", None):
+            self._destroy_group()
             for sh in self.shards:
                 sh.close()
+            self.shards = []
 
     def __del__(self):
         try:
@@ -524,8 +550,7 @@ class StripedIndex:
             raise ValueError(f"queries must be [B][{self.dim}], got {q.shape}")
         B = q.shape[0]
         total = len(self)
-        masks = None
-        keep = []
+        shard_masks = None
         if mask is not None or mask_bits is not None:
             if mask_bits is None:
                 words = np.ascontiguousarray(mask, dtype=np.uint32)
@@ -533,27 +558,25 @@ class StripedIndex:
                     raise ValueError(f"mask needs {(total + 31) // 32} uint32 words, got shape {words.shape}")
                 mask_bits = np.unpackbits(words.view(np.uint8), bitorder="little")[:total].astype(bool)
             bits = np.asarray(mask_bits, dtype=bool)[:total]
-            masks = (ctypes.c_void_p * self.G)()
+            shard_masks = []
             for g in range(self.G):
                 part = bits[g::self.G]
                 pad = (-part.shape[0]) % 32
                 if pad:
                     part = np.concatenate([part, np.zeros(pad, dtype=bool)])
-                w = np.packbits(part, bitorder="little").view(np.uint32) if part.size else np.zeros(1, np.uint32)
-                keep.append(w)
-                masks[g] = w.ctypes.data
-        scores = np.empty((B, int(k)), dtype=np.float32)
-        rows = np.empty((B, int(k)), dtype=np.int64)
-        counts = np.empty(B, dtype=np.int32)
+                shard_masks.append(np.packbits(part, bitorder="little").view(np.uint32) if part.size else np.zeros(1, np.uint32))
         if B > self.max_queries:  # larger than the exchange buffers: slices
+            scores = np.empty((B, int(k)), dtype=np.float32)
+            rows = np.empty((B, int(k)), dtype=np.int64)
+            counts = np.empty(B, dtype=np.int32)
             for lo in range(0, B, self.max_queries):
                 hi = min(B, lo + self.max_queries)
                 scores[lo:hi], rows[lo:hi], counts[lo:hi] = self.query(q[lo:hi], k, ns_code, label_code, path=path,
                                                                        precision=precision, mask_bits=mask_bits)
             return scores, rows, counts
-        p = _QueryParams(B, int(k), int(ns_code), int(label_code), None, int(path), int(precision))
-        _check(self._lib.cv_group_query(self._g, _ptr(q), ctypes.byref(p), masks, _ptr(scores), _ptr(rows), _ptr(counts)))
-        return scores, rows, counts
+        if not 1 <= int(k) <= MAX_K:
+            raise ValueError(f"coddvec: k must be in [1, {MAX_K}] (got {k})")
+        return self._group_query(q, int(k), ns_code, label_code, path, precision, shard_masks)
 
     def delete_rows(self, rows) -> None:
         r = np.ascontiguousarray(rows, dtype=np.int64)

@@ -12,6 +12,7 @@ from oracle import brute_force as bf
 class OracleIndex:
     def __init__(self, dim, metric=bf.METRIC_COSINE, device=0, capacity_rows=0, max_rows=0, row_offset=0, row_stride=1):
         self.dim, self.metric, self.device, self.row_offset = int(dim), int(metric), int(device), int(row_offset)
+        self.row_stride = int(row_stride) or 1
         self._stored = np.zeros((0, dim), np.uint16)
         self._scale = np.zeros(0, np.float32)
         self._ns = np.zeros(0, np.uint32)
@@ -125,3 +126,36 @@ OracleIndex.upsert_device = _upsert_device
 def oracle_merge_keys_device(device, keys_in_ptr, G, B, k_in, k_out, out_ptr, stream=0):
     keys = _view(keys_in_ptr, (G, B, k_in), np.uint64)
     _view(out_ptr, (B, k_out), np.uint64)[...] = bf.merge_keys(keys, k_out)
+
+
+def make_oracle_striped_index():
+    """CPU double of native.StripedIndex: the real routing / numbering logic over OracleIndex shards, with the
+    device group query replaced by per-shard oracle queries + the oracle's key merge."""
+    from codd_query_engine_b200.native import StripedIndex
+
+    class OracleStripedIndex(StripedIndex):
+        def _make_shard(self, dim, **kw):
+            return OracleIndex(dim, **kw)
+
+        def _make_group(self):
+            self._g = None
+
+        def _destroy_group(self):
+            pass
+
+        def _group_query(self, q, k, ns_code, label_code, path, precision, shard_masks):
+            parts = []
+            for g, sh in enumerate(self.shards):
+                if len(sh) == 0:
+                    parts.append(np.zeros((q.shape[0], k), np.uint64))
+                    continue
+                s, r, c = sh.query(q, k, ns_code=ns_code, label_code=label_code,
+                                   mask=None if shard_masks is None else shard_masks[g], path=path)
+                glob = np.where(r >= 0, sh.row_offset + (r - sh.row_offset) * sh.row_stride, 0)  # local -> global row
+                keys = np.where(r >= 0, bf.pack_keys(s.ravel(), glob.ravel()).reshape(r.shape), np.uint64(0))
+                parts.append(keys)
+            best = bf.merge_keys(np.stack(parts), k)
+            scores, rows = bf.unpack_keys(best)
+            return scores, rows, (best != bf.EMPTY_KEY).sum(axis=1).astype(np.int32)
+
+    return OracleStripedIndex

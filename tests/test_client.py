@@ -212,7 +212,8 @@ def test_snapshot_roundtrip(client, tmp_path, request, monkeypatch):
     before = coll.query(query_embeddings=q, n_results=7, where={"namespace": "ns0"})
     before_all = coll.query(query_embeddings=q, n_results=7)
     root = client.persist(str(tmp_path / "snap"))
-    assert sorted(p.name for p in (tmp_path / "snap").iterdir()) == ["metrics_semantic_1"]
+    names = sorted(p.name for p in (tmp_path / "snap").iterdir())
+    assert len(names) == 1 and names[0].startswith("metrics_semantic_1-")  # sanitised name + hash of the real one
     # a new persistent client pointed at the directory sees the same collection and answers identically
     c2 = client_mod.PersistentClient(root)
     try:
@@ -307,3 +308,52 @@ def test_filtered_batches_choose_the_scan_when_the_filter_is_selective(monkeypat
     b = [coll.query(query_embeddings=x[5 + i], n_results=4, where={"namespace": "rare"})["ids"][0] for i in range(4)]
     assert a["ids"] == b
     c.reset()
+
+
+def test_snapshot_is_replaced_atomically_and_validated(client, tmp_path):
+    """A re-save never leaves old metadata next to new data, names that sanitise alike keep separate directories,
+    deleted collections do not come back, and a truncated data file is refused."""
+    a = client.get_or_create_collection("a/b", metadata=COSINE)
+    b = client.get_or_create_collection("a_b", metadata=COSINE)
+    a.upsert(ids=["x", "y"], embeddings=vecs(2, d=16, seed=1))
+    b.upsert(ids=["z"], embeddings=vecs(1, d=16, seed=2))
+    root = client.persist(str(tmp_path / "snap"))
+    assert len(list((tmp_path / "snap").iterdir())) == 2
+    a.upsert(ids=["w"], embeddings=vecs(1, d=16, seed=3))
+    client.delete_collection("a_b")
+    client.persist(root)
+    dirs = sorted(p.name for p in (tmp_path / "snap").iterdir())
+    assert len(dirs) == 1 and not any(".tmp-" in d or ".old-" in d for d in dirs)
+    c2 = client_mod.PersistentClient(root)
+    try:
+        assert [c.name for c in c2.list_collections()] == ["a/b"] and c2.get_collection("a/b").count() == 3
+    finally:
+        c2.reset()
+    data = tmp_path / "snap" / dirs[0] / "rows.bf16"
+    data.write_bytes(data.read_bytes()[:-8])
+    with pytest.raises(ValueError, match="corrupt"):
+        client_mod.Collection.load(str(tmp_path / "snap" / dirs[0]))
+
+
+def test_failed_upsert_keeps_tombstones_and_metadata_updates_reach_the_device(client):
+    coll = client.get_or_create_collection("adv", metadata=COSINE)
+    x = vecs(6, d=16, seed=4)
+    coll.upsert(ids=list("abcdef"), embeddings=x, metadatas=[{"namespace": "n1", "category": "k"}] * 6)
+    coll.delete(ids=["b", "c"])
+    bad = vecs(2, d=16, seed=5)
+    bad[1, 3] = np.nan
+    with pytest.raises(ValueError):
+        coll.upsert(ids=["g", "h"], embeddings=bad)           # rejected: the two free slots must still be free
+    assert sorted(coll._free_rows) == [1, 2] and coll.count() == 4
+    res = coll.query(query_embeddings=x[1:2], n_results=6)      # deleted rows never come back, with or without a mask
+    assert None not in res["ids"][0] and "b" not in res["ids"][0] and len(res["ids"][0]) == 4
+    coll.upsert(ids=["g"], embeddings=x[1:2])                   # reuses a tombstoned slot
+    assert coll.count() == 5 and coll.query(query_embeddings=x[1:2], n_results=1)["ids"] == [["g"]]
+    # metadata-only update that moves a row to another namespace: query(where=) and get(where=) must agree
+    coll.update(ids=["a"], metadatas=[{"namespace": "n2"}])
+    assert coll.get(ids=["a"])["metadatas"] == [{"namespace": "n2", "category": "k"}]      # merged, not replaced
+    assert coll.query(query_embeddings=x[:1], n_results=3, where={"namespace": "n2"})["ids"] == [["a"]]
+    assert "a" not in coll.query(query_embeddings=x[:1], n_results=6, where={"namespace": "n1"})["ids"][0]
+    assert coll.get(where={"namespace": "n2"})["ids"] == ["a"]
+    coll.update(ids=["d"], embeddings=x[3:4] * 2, metadatas=[{"extra": 1}])                  # with embeddings: merged too
+    assert coll.get(ids=["d"])["metadatas"] == [{"namespace": "n1", "category": "k", "extra": 1}]
