@@ -39,17 +39,20 @@ def _deps_mtime() -> float:
     return max(f.stat().st_mtime for f in files)
 
 
-def _compile(unit: str, force: bool) -> Path:
+def _compile(unit: str, force: bool, checked: bool = False) -> Path:
     src = CSRC / unit
-    obj = OBJ_DIR / (src.stem + ".o")
-    log = OBJ_DIR / (src.stem + ".ptxas.log")
+    obj_dir = OBJ_DIR.parent / "obj_checked" if checked else OBJ_DIR
+    obj_dir.mkdir(parents=True, exist_ok=True)
+    obj = obj_dir / (src.stem + ".o")
+    log = obj_dir / (src.stem + ".ptxas.log")
     newest = max(src.stat().st_mtime, _deps_mtime())
     if not force and obj.exists() and obj.stat().st_mtime >= newest:
         return obj
     env = dict(os.environ)
     env.pop("CC", None)
     env.pop("CXX", None)
-    cmd = [_nvcc(), *NVCC_FLAGS, "-ccbin", "/usr/bin/g++", "-c", str(src), "-o", str(obj)]
+    extra = os.environ.get("CODDVEC_NVCC_EXTRA", "").split()  # (-D switches of A/B experiment builds)
+    cmd = [_nvcc(), *NVCC_FLAGS, *(["-DCV_CHECKED"] if checked else []), *extra, "-ccbin", "/usr/bin/g++", "-c", str(src), "-o", str(obj)]
     proc = subprocess.run(cmd, capture_output=True, text=True, env=env)
     log.write_text(proc.stderr)
     if proc.returncode != 0:
@@ -57,11 +60,14 @@ def _compile(unit: str, force: bool) -> Path:
     return obj
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
+def build(force: bool = False, verbose: bool = False, checked: bool = False) -> Path:
+    """checked=True: libcoddvec_checked.so, the same sources with -DCV_CHECKED (device-side bounds assertions that
+    trap) -- select it with CODDVEC_LIB for the assertion pass that stands in for compute-sanitizer."""
     OBJ_DIR.mkdir(parents=True, exist_ok=True)
+    OUT = PKG / ("libcoddvec_checked.so" if checked else "libcoddvec.so")
     units = [u for u in UNITS if (CSRC / u).exists()]
     with ThreadPoolExecutor(max_workers=min(len(units), os.cpu_count() or 4)) as pool:
-        objs = list(pool.map(lambda u: _compile(u, force), units))
+        objs = list(pool.map(lambda u: _compile(u, force, checked), units))
     if force or not OUT.exists() or any(o.stat().st_mtime > OUT.stat().st_mtime for o in objs):
         env = dict(os.environ)
         env.pop("CC", None)
@@ -77,4 +83,4 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose=True)
+    build(force="--force" in sys.argv, verbose=True, checked="--checked" in sys.argv)

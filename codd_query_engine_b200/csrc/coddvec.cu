@@ -321,7 +321,7 @@ int enqueue_query(cv_index* idx, QueryCtx* c, cudaStream_t stream, const float* 
         int rc0 = c->d_local.reserve(static_cast<size_t>(B) * k);
         if (rc0) return rc0;
         CV_CUDA(cudaMemsetAsync(c->d_local.p, 0, sizeof(uint64_t) * B * k, stream));
-        k_exchange_merge<<<B, 256, 0, stream>>>(*px, seq, 0, c->d_local.p, k, d_out);
+        k_exchange_merge<<<std::min(B, kExchangeCtas), 256, 0, stream>>>(*px, seq, 0, c->d_local.p, k, d_out, B);
         CV_CUDA(cudaGetLastError());
         idx->launches.fetch_add(1);
         return CV_OK;
@@ -378,7 +378,7 @@ int enqueue_query(cv_index* idx, QueryCtx* c, cudaStream_t stream, const float* 
         int rc = mma_enqueue(m, c->mma, &idx->launches);
         if (rc != 0) return fail(rc, "%s", mma_error().c_str());
         if (exchange) {
-            k_exchange_merge<<<B, 256, 0, stream>>>(*px, seq, 0, c->d_local.p, k, d_out);
+            k_exchange_merge<<<std::min(B, kExchangeCtas), 256, 0, stream>>>(*px, seq, 0, c->d_local.p, k, d_out, B);
             CV_CUDA(cudaGetLastError());
             idx->launches.fetch_add(1);
         }
@@ -917,6 +917,11 @@ struct cv_group {
     std::mutex mu;                   // one batch in flight per group: all shards see the same batches in the same order
     uint64_t seq = 0;
     bool broken = false;             // a shard failed mid-batch: its peers' flags can no longer be trusted
+    // Shapes every shard has already served: buffers (query staging, K2 partials, K3 scratch, masks) grow on first
+    // use, and cudaMalloc / cudaFree wait for the device -- which must not happen while a peer's kernel is already
+    // spinning on this shard's keys.  A new shape is first run on every shard WITHOUT the exchange ("priming").
+    int primed_B = 0, primed_k = 0;
+    unsigned primed_paths = 0;       // bit per (path, precision, filtered)
 };
 
 extern "C" {
@@ -1181,6 +1186,17 @@ int cv_group_query(cv_group* grp, const float* q, const cv_query_params* p, cons
     if ((rc = check_finite_queries(grp->shards[0], q, p->n_queries))) return rc;
     std::lock_guard<std::mutex> lock(grp->mu);
     if (grp->broken) return fail(CV_ERR_CUDA, "a shard of this striped collection failed earlier; the collection must be reopened");
+    const unsigned path_bit = 1u << ((p->path * 3 + p->precision) * 2 + (masks != nullptr ? 1 : 0));
+    if (p->n_queries > grp->primed_B || p->k > grp->primed_k || !(grp->primed_paths & path_bit)) {
+        for (int g = 0; g < G; ++g) {
+            PendingQuery warm;
+            if ((rc = query_host_begin(grp->shards[g], q, p, masks ? masks[g] : nullptr, nullptr, 0, &warm))) return rc;
+            if ((rc = query_host_finish(&warm, nullptr, nullptr, nullptr))) return rc;
+        }
+        grp->primed_B = std::max(grp->primed_B, p->n_queries);
+        grp->primed_k = std::max(grp->primed_k, p->k);
+        grp->primed_paths |= path_bit;
+    }
     const uint64_t seq = ++grp->seq;
     std::vector<PendingQuery> pend(G);
     // shard 0 last: it is the one whose merged result is read, and its kernel waits for everybody else's keys anyway

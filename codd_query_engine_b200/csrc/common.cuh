@@ -7,6 +7,23 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// CV_CHECKED builds (python -m codd_query_engine_b200.build --checked -> libcoddvec_checked.so) turn the index
+// arithmetic the kernels rely on into device-side assertions that trap: the bounds-check pass this project runs in
+// place of compute-sanitizer, which is closed on the GPU pool (profiles/README.md).
+#ifdef CV_CHECKED
+#include <cstdio>
+#define CV_ASSERT(cond)                                                                                          \
+    do {                                                                                                         \
+        if (!(cond)) {                                                                                           \
+            printf("CV_ASSERT failed: %s (%s:%d) block %d thread %d\n", #cond, __FILE__, __LINE__, (int)blockIdx.x, \
+                   (int)threadIdx.x);                                                                            \
+            __trap();                                                                                            \
+        }                                                                                                        \
+    } while (0)
+#else
+#define CV_ASSERT(cond) ((void)0)
+#endif
+
 namespace cv {
 
 constexpr int kMaxK = 128;
@@ -120,8 +137,10 @@ __device__ __forceinline__ uint64_t warp_prune_impl(uint64_t* buf, int k, int la
     }
     __syncwarp();
 #pragma unroll
-    for (int j = 0; j < PER; ++j)
+    for (int j = 0; j < PER; ++j) {
+        CV_ASSERT(rank[j] >= 0 && rank[j] < CAP);
         if (rank[j] < k) buf[rank[j]] = mine[j];
+    }
     __syncwarp();
     return buf[k - 1];
 }
@@ -137,6 +156,7 @@ __device__ __forceinline__ uint64_t warp_prune(uint64_t* buf, int cap, int k, in
 // prune happened, in which case `kth` holds the new k-th best key of this buffer.
 __device__ __forceinline__ bool warp_buf_append(uint64_t* buf, int cap, int k, uint64_t key, int lane, int& cnt,
                                                 uint64_t& kth) {
+    CV_ASSERT(cnt >= 0 && cnt < cap);
     if (lane == 0) buf[cnt] = key;
     if (++cnt < cap) return false;
     __syncwarp();
@@ -211,6 +231,7 @@ __device__ __forceinline__ void block_select_topk(Src src, int m, int k, uint64_
         for (int u = 0; u < U; ++u) {
             if (key[u] != 0ull && key[u] >= s_tau) {
                 int p = atomicAdd(cnt, 1);
+                CV_ASSERT(p >= 0 && p < kSelCap);
                 buf[p] = key[u];
                 ++mine;
             }
@@ -276,24 +297,31 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
     return t;
 }
 
-// Whole block.  local[0..k) (shared memory, this GPU's final top-k for global query index q) is published
-// to all ranks; on return buf[0..k) holds the merged top-k of all ranks.  local may alias buf.
-__device__ __forceinline__ void exchange_and_merge(const PeerExchange& px, uint64_t seq, int q, const uint64_t* local,
-                                                   int k, uint64_t* buf, int* cnt) {
+// Whole block.  Publish: local[0..k) (this GPU's final top-k for global query index q; shared or global memory) goes
+// to every rank's buffer, then this rank's flag for q is raised everywhere.
+__device__ __forceinline__ void exchange_publish(const PeerExchange& px, uint64_t seq, int q, const uint64_t* local, int k) {
+    CV_ASSERT(q >= 0 && q < px.max_q && k <= px.max_k && px.rank < px.world && px.world <= kMaxPeers);
     const int G = px.world;
     const size_t flag_words = static_cast<size_t>(G) * px.max_q;
     const size_t slot_words = static_cast<size_t>(G) * px.max_q * px.max_k;
     const size_t key_off = flag_words + (seq & 1ull) * slot_words + (static_cast<size_t>(px.rank) * px.max_q + q) * px.max_k;
-    // 1. peer stores of my k keys (coalesced 8-byte stores over NVLink; my own copy goes the same way)
+    // peer stores of my k keys (coalesced 8-byte stores over NVLink; my own copy goes the same way)
     for (int i = threadIdx.x; i < G * k; i += blockDim.x) {
         const int g = i / k, j = i - g * k;
         st_relaxed_sys(px.base[g] + key_off + j, local[j]);
     }
     __threadfence_system();
     __syncthreads();
-    // 2. raise my flag on every rank, then wait for every rank's flag in my own buffer
     if (static_cast<int>(threadIdx.x) < G)
         st_release_sys(px.base[threadIdx.x] + static_cast<size_t>(px.rank) * px.max_q + q, seq);
+}
+
+// Whole block.  Wait for every rank's flag for q in my own buffer, then merge the G lists that landed there: on
+// return buf[0..k) holds the merged top-k of all ranks.
+__device__ __forceinline__ void exchange_wait_merge(const PeerExchange& px, uint64_t seq, int q, int k, uint64_t* buf, int* cnt) {
+    const int G = px.world;
+    const size_t flag_words = static_cast<size_t>(G) * px.max_q;
+    const size_t slot_words = static_cast<size_t>(G) * px.max_q * px.max_k;
     if (static_cast<int>(threadIdx.x) < G) {
         const uint64_t* f = px.base[px.rank] + static_cast<size_t>(threadIdx.x) * px.max_q + q;
         // bounded: a peer that never publishes (its launch failed, its process died) must not hang this GPU --
@@ -309,13 +337,19 @@ __device__ __forceinline__ void exchange_and_merge(const PeerExchange& px, uint6
         }
     }
     __syncthreads();
-    // 3. merge the G lists that landed here
     const uint64_t* mine = px.base[px.rank] + flag_words + (seq & 1ull) * slot_words;
     auto src = [&](int i) {
         const int g = i / k, j = i - g * k;
         return ld_relaxed_sys(mine + (static_cast<size_t>(g) * px.max_q + q) * px.max_k + j);
     };
     block_select_topk<1>(src, G * k, k, 0ull, buf, cnt);
+}
+
+// Publish + wait + merge for one query (K2's last CTA).  local may alias buf.
+__device__ __forceinline__ void exchange_and_merge(const PeerExchange& px, uint64_t seq, int q, const uint64_t* local,
+                                                   int k, uint64_t* buf, int* cnt) {
+    exchange_publish(px, seq, q, local, k);
+    exchange_wait_merge(px, seq, q, k, buf, cnt);
 }
 #endif  // __CUDACC__
 

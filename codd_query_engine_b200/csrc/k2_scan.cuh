@@ -185,6 +185,7 @@ __device__ __forceinline__ void publish_and_final_merge(const uint64_t* lists, i
         const int nsurv = __syncthreads_count(static_cast<int>(threadIdx.x) < k && selbuf[threadIdx.x] != 0ull);
         if (threadIdx.x == 0) s_pos = nsurv ? atomicAdd(counter + 1 + b, static_cast<unsigned int>(nsurv)) : 0u;
         __syncthreads();
+        CV_ASSERT(nsurv <= k && s_pos + nsurv <= stride);
         if (static_cast<int>(threadIdx.x) < nsurv) partial[b * stride + s_pos + threadIdx.x] = selbuf[threadIdx.x];
         __syncthreads();
     }
@@ -198,6 +199,7 @@ __device__ __forceinline__ void publish_and_final_merge(const uint64_t* lists, i
     for (int b = 0; b < QBn; ++b) {
         const uint64_t* pb = partial + b * stride;
         const int m = static_cast<int>(__ldcg(counter + 1 + b));
+        CV_ASSERT(m >= 0 && static_cast<size_t>(m) <= stride);
         if (warp == 0) {
             const uint64_t hb = m > 512 ? heads_bound_key(heads + b * kHeadSlots, k, lane) : 0ull;
             if (lane == 0) s_hb = hb;
@@ -379,6 +381,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_topk(ScanArgs a) {
 #pragma unroll
             for (int s = 0; s < S; ++s) my_row = (s == my_slot) ? rows[s] : my_row;
         }
+        CV_ASSERT(!(FAST || DENSE || row_valid(my_row)) || static_cast<int64_t>(my_row) < a.n);
         const float sc = (FAST || DENSE || row_valid(my_row)) ? __ldg(a.scale + my_row) : 0.0f;
 
         float acc[V];
@@ -570,6 +573,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_topk(ScanArgs a) {
             if (ok3) ring[(t + __popc(w3 & lt_mask)) & (kRingCap - 1)] = base + 3;
             tail = t + __popc(w3);
             __syncwarp();
+            CV_ASSERT(tail - head <= static_cast<uint32_t>(kRingCap));
             while (tail - head >= static_cast<uint32_t>(S)) {
                 consume(head, S);
                 head += S;
@@ -793,17 +797,24 @@ __global__ void __launch_bounds__(256) k_merge_keys(const uint64_t* in, int G, i
     for (int j = threadIdx.x; j < k_out; j += blockDim.x) out[static_cast<size_t>(b) * k_out + j] = selbuf[j];
 }
 
-// Batched path: K3 leaves this GPU's top-k per query in `local` [B][k]; one CTA per query does the
-// fused NVLink exchange + cross-GPU merge.
+// Batched path: K3 leaves this GPU's top-k per query in `local` [nq][k]; a FEW CTAs (kExchangeCtas at most) do the
+// fused NVLink exchange + cross-GPU merge, each for the queries b = blockIdx.x, blockIdx.x + gridDim.x, ...: all of a
+// CTA's queries are published before it waits for any, so the waits cannot cycle, and only a handful of SMs sit in
+// the spin-wait while a slower peer is still scanning.
+constexpr int kExchangeCtas = 32;
 __global__ void __launch_bounds__(256) k_exchange_merge(PeerExchange px, uint64_t seq, int q_base, const uint64_t* local,
-                                                        int k, uint64_t* out) {
+                                                        int k, uint64_t* out, int nq) {
     __shared__ __align__(16) uint64_t selbuf[kSelCap];
     __shared__ int s_cnt;
-    const int b = blockIdx.x;
-    for (int j = threadIdx.x; j < k; j += blockDim.x) selbuf[j] = local[static_cast<size_t>(b) * k + j];
-    __syncthreads();
-    exchange_and_merge(px, seq, q_base + b, selbuf, k, selbuf, &s_cnt);
-    for (int j = threadIdx.x; j < k; j += blockDim.x) out[static_cast<size_t>(b) * k + j] = selbuf[j];
+    for (int b = blockIdx.x; b < nq; b += gridDim.x) {
+        exchange_publish(px, seq, q_base + b, local + static_cast<size_t>(b) * k, k);
+        __syncthreads();
+    }
+    for (int b = blockIdx.x; b < nq; b += gridDim.x) {
+        exchange_wait_merge(px, seq, q_base + b, k, selbuf, &s_cnt);
+        for (int j = threadIdx.x; j < k; j += blockDim.x) out[static_cast<size_t>(b) * k + j] = selbuf[j];
+        __syncthreads();
+    }
 }
 #endif  // CV_MAIN_TU
 

@@ -85,6 +85,7 @@ struct KArgs {
     uint64_t corpus_hint;
     uint32_t row_stride;   // global row = row_offset + local row * row_stride (1 = dense block, G = cyclic shard)
     int scale_bounded;     // 1: every row scale is 0, NaN or within 2^-7 of 1 (enables the raw-dot prefilter)
+    int exact_heads;       // 1: in-scan threshold refreshes use the exact k-th largest head (large batches)
     // fused query preparation (q_resident only): the CTA normalises its 128 raw queries itself and writes the bf16
     // tile (and, with `split`, the bf16 residual tile) straight into the swizzled shared-memory layout
     const float* q_raw;    // [B][D] fp32 raw queries of this slice, or nullptr (the tile comes from tmap_q)
@@ -97,7 +98,7 @@ struct KArgs {
     uint64_t* cand;        // [Bpad][cand_ld]
     int cand_ld;           // P * k
     uint32_t* cnt;         // [Bpad] survivors appended per query
-    uint32_t* done;        // [q_tiles * CG] CTAs of the group that have published
+    uint32_t* done;        // [Bpad] list owners of the query that have published (the last one merges)
     uint64_t* out;         // [B][k] final keys of this slice
     unsigned long long* dbg;  // nullptr, or 4 words (atomicMax): prep ns, publish ns, merge ns, survivors per query
 };
@@ -256,6 +257,12 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// Fire-and-forget maximum (RED, not ATOM: the issuing warp must not wait an L2 round trip per published threshold --
+// nvcc turned the value-less atomicMax of this kernel into a returning ATOMG, which cost 35-100 us per batch).
+__device__ __forceinline__ void red_max_u32(uint32_t* p, uint32_t v) {
+    asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // order-preserving float <-> uint32 (same mapping as the high word of a result key); 0 = "nothing yet"
 __device__ __forceinline__ uint32_t ord_of(float f) {
     uint32_t u = __float_as_uint(f + 0.0f);
@@ -323,6 +330,43 @@ __device__ __forceinline__ uint32_t heads_bound(const uint32_t* row, int P, int 
         }
     }
     return min(bound, m);
+}
+
+// Exact version for short lists (KH <= 16 registers): the k-th LARGEST of the P heads.  At least k owners hold a row
+// that good, so it bounds the global k-th best from below -- and it is the tightest bound the heads give (the
+// grouped minimum above sits ~3x deeper in the ranking), which is what keeps the fused tail's survivor lists short.
+template <int KH>
+__device__ __forceinline__ uint32_t heads_kth(const uint32_t* row, int P, int k) {
+    if (P < k) return 0u;
+    uint32_t T[KH];  // right-aligned descending top-k; the slots before it are never-beaten sentinels
+#pragma unroll
+    for (int j = 0; j < KH; ++j) T[j] = (j < KH - k) ? 0xFFFFFFFFu : 0u;
+    const int nv = (P + 3) / 4;
+#pragma unroll 1
+    for (int v0 = 0; v0 < nv; v0 += 8) {
+        uint4 w[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            w[u] = (v0 + u < nv) ? __ldcg(reinterpret_cast<const uint4*>(row) + v0 + u) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const uint32_t x[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (x[e] > T[KH - 1]) {
+                    uint32_t cur = x[e];
+#pragma unroll
+                    for (int j = 0; j < KH; ++j) {
+                        const bool gt = cur > T[j];
+                        const uint32_t hi = gt ? cur : T[j];
+                        cur = gt ? T[j] : cur;
+                        T[j] = hi;
+                    }
+                }
+            }
+        }
+    }
+    return T[KH - 1];
 }
 
 // register-resident descending list: branch-free bubble insertion, no memory traffic
@@ -468,6 +512,7 @@ __device__ __forceinline__ void prep_query_tile(unsigned char* sm_q, const float
             for (int j = 0; j < 2; ++j) {
                 const int c = lane + 32 * j;
                 if (c < nchunks) {
+                    CV_ASSERT(r >= 0 && r < kQ && (c >> 3) < kblocks);
                     uint32_t hi[4], lo[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
@@ -554,11 +599,13 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
     }
     if (warp == 1) tmem_alloc<CG>(smem_u32(tmem_slot), kCols);
     const bool fused_prep = a.q_raw != nullptr;  // (q_resident only)
+#ifndef CV_K3_NO_INKERNEL_PREP
     if (fused_prep) {
         const uint64_t t0 = a.dbg ? global_timer_ns() : 0;
         prep_query_tile<64 + 32 * EW>(sm_q, a.q_raw, (qt * CG + static_cast<int>(rank)) * kQ, a.B, a.D, a.kblocks, a.cosine, a.split);
         if (a.dbg && (threadIdx.x & 31) == 0) atomicMax(a.dbg, global_timer_ns() - t0);
     }
+#endif
     tc_fence_before();
     if (CG == 2) cluster_sync(); else __syncthreads();  // barriers, TMEM address and both CTAs' query tiles are ready
     tc_fence_after();
@@ -641,6 +688,7 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
         const int qglobal = (qt * CG + static_cast<int>(rank)) * kQ + qlane;
         const int owner = half * a.P + p;                // this thread's slot among the lists / heads of its query
         const int owners = a.P * kHalves;
+        CV_ASSERT(qglobal < a.Bpad && owner < owners && kHalves * ((a.P + 3) / 4 * 4) <= kHeadsLd && a.k <= (KREG > 0 ? KREG : kMaxK));
         // (heads bound: a thread ranks the heads of its OWN column half only -- k distinct owners there still each
         // hold a row at least that good, and the refresh costs what it does with four epilogue warps)
         const uint32_t* const my_heads = a.heads + static_cast<size_t>(qglobal) * kHeadsLd + half * ((a.P + 3) / 4 * 4);
@@ -710,9 +758,20 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
             if (KREG > 0 && share) {
                 // heads bound at tiles 1, 4, 16, 64, ... of this CTA and once more before its last tile (the fused
                 // tail publishes the keys above the bound folded in by then)
+#ifdef CV_K3_NO_LAST_REFRESH
+                const bool last = false;
+#else
                 const bool last = tcount + 1 == my_tiles && my_tiles > 2;
+#endif
                 if (tcount == next_refresh || last) {
-                    if (tcount * 8 <= my_tiles || last) fold_shared(heads_bound(my_heads, a.P, a.k));
+                    // The exact k-th largest head costs ~7 us of this thread's time.  Before the last tile it always
+                    // pays (it decides how many keys the fused tail has to merge).  During the scan it pays when
+                    // candidate handling bounds the kernel -- large batches: a tight bound early spares every CTA
+                    // most of its list convergence (B = 256 at 1M rows: 0.24 -> 0.20 ms) -- and costs 5 % when the
+                    // scan is HBM-bound, where the cheap grouped bound is used instead.
+                    const bool exact = KREG <= 16 && (last || a.exact_heads != 0);
+                    if (last || tcount * 8 <= my_tiles)
+                        fold_shared(exact ? heads_kth<KR>(my_heads, a.P, a.k) : heads_bound(my_heads, a.P, a.k));
                     if (tcount == next_refresh) next_refresh *= 4;
                 }
             }
@@ -785,7 +844,7 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
                                 changed = true;
                             }
                         }
-                        if (changed && share && L[KR - 1] != 0ull) atomicMax(a.gthr + qglobal, ord_of(thr_local));
+                        if (changed && share && L[KR - 1] != 0ull) red_max_u32(a.gthr + qglobal, ord_of(thr_local));
                     }
                 } else if (__any_sync(kFullMask, any)) {
                     // large k: the lists live in global memory (L1/L2 resident) and the whole warp inserts
@@ -817,7 +876,7 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
                         if (lane == src && changed) {
                             thr_local = local_src;
                             thr = thr_src;
-                            if (share && local_src > -INFINITY) atomicMax(a.gthr + qglobal, ord_of(local_src));
+                            if (share && local_src > -INFINITY) red_max_u32(a.gthr + qglobal, ord_of(local_src));
                         }
                     }
                 }
@@ -833,70 +892,67 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
         if (fused_tail) {
             // ---- fused tail: no merge launch.  A single list owner: its list is final.  Otherwise every owner
             // publishes the keys that can still be in the global top-k -- score >= the largest shared lower bound it
-            // has folded in (every CTA's k-th best through gthr, the heads bound refreshed before the last tile): both
-            // bound the global k-th best from below, so every global top-k key survives in its owner -- to
-            // cand[q][...] (one atomicAdd per owner reserves the range; a few dozen keys per query in the whole
-            // grid), and the last CTA of the group (threadfence + counter) merges its 128 queries, thread = query.
+            // knows (every CTA's k-th best through gthr, the heads bound refreshed before the last tile): both bound
+            // the global k-th best from below, so every global top-k key survives in its owner.
             if (owners == 1) {
                 if (live) {
 #pragma unroll
                     for (int j = 0; j < KR; ++j)
                         if (j >= KR - a.k) a.out[static_cast<size_t>(qglobal) * a.k + (j - (KR - a.k))] = L[j];
                 }
-            } else {
-                volatile uint32_t* const s_last = tmem_slot + 2;  // (spare word of the dynamic carve-up: no static shared memory)
+            } else if (live) {
+                // Publish, then merge wherever the LAST owner of a query happens to run: every owner appends its
+                // surviving keys to cand[q][...] (atomicAdd on cnt[q] reserves the range), fences, and bumps the
+                // query's "owners published" counter; the thread that completes the count merges that query on
+                // the spot.  The owners of a query finish within microseconds of each other all over the grid, so
+                // the B merges run in parallel on many SMs instead of queueing in one CTA.
                 const uint64_t t_tail = a.dbg ? global_timer_ns() : 0;
-                const int group = qt * CG + static_cast<int>(rank);
-                if (live) {
-                    const uint32_t g = max(g_seen, g_next);
-                    int ns = 0;
+                const uint32_t g = max(g_seen, __ldcg(a.gthr + qglobal));
+                int ns = 0;
 #pragma unroll
-                    for (int j = 0; j < KR; ++j)
-                        ns += (j >= KR - a.k && L[j] != 0ull && static_cast<uint32_t>(L[j] >> 32) >= g) ? 1 : 0;
-                    if (ns) {  // the list is sorted: the survivors are its first ns entries
-                        const uint32_t pos = atomicAdd(a.cnt + qglobal, static_cast<uint32_t>(ns));
-                        uint64_t* dst = a.cand + static_cast<size_t>(qglobal) * a.cand_ld + pos;
+                for (int j = 0; j < KR; ++j)
+                    ns += (j >= KR - a.k && L[j] != 0ull && static_cast<uint32_t>(L[j] >> 32) >= g) ? 1 : 0;
+                if (ns) {  // the list is sorted: the survivors are its first ns entries
+                    const uint32_t pos = atomicAdd(a.cnt + qglobal, static_cast<uint32_t>(ns));
+                    CV_ASSERT(ns <= a.k && pos + ns <= static_cast<uint32_t>(a.cand_ld));
+                    uint64_t* dst = a.cand + static_cast<size_t>(qglobal) * a.cand_ld + pos;
 #pragma unroll
-                        for (int j = 0; j < KR; ++j) {
-                            const int i = j - (KR - a.k);
-                            if (i >= 0 && i < ns) __stcg(dst + i, L[j]);
-                        }
+                    for (int j = 0; j < KR; ++j) {
+                        const int i = j - (KR - a.k);
+                        if (i >= 0 && i < ns) __stcg(dst + i, L[j]);
                     }
                 }
                 __threadfence();
-                asm volatile("bar.sync 1, %0;" ::"n"(kEpi) : "memory");
-                if (et == 0) *s_last = atomicAdd(a.done + group, 1u) == static_cast<unsigned>(a.P - 1) ? 1u : 0u;
-                asm volatile("bar.sync 1, %0;" ::"n"(kEpi) : "memory");
+                const bool last_owner = atomicAdd(a.done + qglobal, 1u) == static_cast<unsigned>(owners - 1);
                 if (a.dbg && lane == 0) atomicMax(a.dbg + 1, global_timer_ns() - t_tail);
-                if (*s_last && half == 0) {
+                if (last_owner) {
                     __threadfence();
                     const uint64_t t_merge = a.dbg ? global_timer_ns() : 0;
-                    if (live) {
-                        const uint32_t m = __ldcg(a.cnt + qglobal);
-                        if (a.dbg) atomicMax(a.dbg + 3, static_cast<unsigned long long>(m));
-                        const uint64_t* src = a.cand + static_cast<size_t>(qglobal) * a.cand_ld;
+                    const uint32_t m = __ldcg(a.cnt + qglobal);
+                    CV_ASSERT(m <= static_cast<uint32_t>(a.cand_ld));
+                    if (a.dbg) atomicMax(a.dbg + 3, static_cast<unsigned long long>(m));
+                    const uint64_t* src = a.cand + static_cast<size_t>(qglobal) * a.cand_ld;
 #pragma unroll
-                        for (int j = 0; j < KR; ++j) L[j] = (j < KR - a.k) ? ~0ull : 0ull;
+                    for (int j = 0; j < KR; ++j) L[j] = (j < KR - a.k) ? ~0ull : 0ull;
+                    constexpr int U = KR <= 16 ? 16 : 8;  // keys in flight per L2 round trip
 #pragma unroll 1
-                        constexpr int U = KR <= 16 ? 16 : 8;  // keys in flight per L2 round trip
-                        for (uint32_t i0 = 0; i0 < m; i0 += U) {
-                            uint64_t kk[U];
+                    for (uint32_t i0 = 0; i0 < m; i0 += U) {
+                        uint64_t kk[U];
 #pragma unroll
-                            for (int u = 0; u < U; ++u) kk[u] = (i0 + u < m) ? __ldcg(src + i0 + u) : 0ull;
+                        for (int u = 0; u < U; ++u) kk[u] = (i0 + u < m) ? __ldcg(src + i0 + u) : 0ull;
 #pragma unroll
-                            for (int u = 0; u < U; ++u)
-                                if (kk[u] > L[KR - 1]) list_insert_regs<KR>(L, kk[u]);
-                        }
-#pragma unroll
-                        for (int j = 0; j < KR; ++j)
-                            if (j >= KR - a.k) a.out[static_cast<size_t>(qglobal) * a.k + (j - (KR - a.k))] = L[j];
-                        // every CTA of the group is done: leave the shared state zero for the next launch
-                        a.cnt[qglobal] = 0u;
-                        a.gthr[qglobal] = 0u;
-                        for (int v = 0; v < kHalves * ((a.P + 3) / 4); ++v) reinterpret_cast<uint4*>(head_row)[v] = make_uint4(0u, 0u, 0u, 0u);
+                        for (int u = 0; u < U; ++u)
+                            if (kk[u] > L[KR - 1]) list_insert_regs<KR>(L, kk[u]);
                     }
-                    if (et == 0) a.done[group] = 0u;
-                    if (a.dbg && lane == 0) atomicMax(a.dbg + 2, global_timer_ns() - t_merge);
+#pragma unroll
+                    for (int j = 0; j < KR; ++j)
+                        if (j >= KR - a.k) a.out[static_cast<size_t>(qglobal) * a.k + (j - (KR - a.k))] = L[j];
+                    // every owner of this query is done: leave its shared state zero for the next launch
+                    a.cnt[qglobal] = 0u;
+                    a.done[qglobal] = 0u;
+                    a.gthr[qglobal] = 0u;
+                    for (int v = 0; v < kHalves * ((a.P + 3) / 4); ++v) reinterpret_cast<uint4*>(head_row)[v] = make_uint4(0u, 0u, 0u, 0u);
+                    if (a.dbg) atomicMax(a.dbg + 2, global_timer_ns() - t_merge);
                 }
             }
         } else if (KREG > 0) {
@@ -918,18 +974,20 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
 
 using MmaKernel = void (*)(const CUtensorMap, const CUtensorMap, const KArgs);
 
-// k <= 16: four or eight epilogue warps (the host picks by batch size); k <= 32: eight; longer register lists and the
-// shared- / global-memory lists keep four (register budget: 65536 / 320 threads = 204 per thread).
+// k <= 16: four or eight epilogue warps (the host picks; four by default); everything else four (register budget of
+// eight: 65536 / 320 threads = 204 per thread).
 template <int CG>
 inline MmaKernel pick_mma_kernel(bool dump, int k, int ew) {
     if (dump) return k_mma_topk<true, 0, CG, 4>;
+#ifndef CV_K3_NO_KREG10
     if (k <= 10) return ew == 4 ? static_cast<MmaKernel>(k_mma_topk<false, 10, CG, 4>) : static_cast<MmaKernel>(k_mma_topk<false, 10, CG, 8>);
+#endif
     if (k <= 16) return ew == 4 ? static_cast<MmaKernel>(k_mma_topk<false, 16, CG, 4>) : static_cast<MmaKernel>(k_mma_topk<false, 16, CG, 8>);
-    if (k <= 32) return k_mma_topk<false, 32, CG, 8>;
+    if (k <= 32) return k_mma_topk<false, 32, CG, 4>;
     if (k <= 64) return k_mma_topk<false, 64, CG, 4>;
     return k_mma_topk<false, 0, CG, 4>;
 }
-inline int mma_kernel_epilogue_warps(bool dump, int k, int ew) { return (dump || k > 32) ? 4 : (k <= 16 && ew == 4 ? 4 : 8); }
+inline int mma_kernel_epilogue_warps(bool dump, int k, int ew) { return (!dump && k <= 16 && ew == 8) ? 8 : 4; }
 
 MmaKernel pick_mma_kernel_cg2(bool dump, int k, int ew);  // k3_inst_cg2.cu
 

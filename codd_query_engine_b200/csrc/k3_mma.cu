@@ -72,11 +72,11 @@ int raise_smem_limit(MmaKernel kernel) {
     return 0;
 }
 
-// Self-resetting cross-CTA state for `queries` queries: heads [q][kHeadsLd], gthr [q], cnt [q], done [q / kQ + 1].
-// All of it is zero between launches (the fused tail's last CTA per group clears what its group dirtied), so it is
-// zeroed once, when (re)allocated.
+// Self-resetting cross-CTA state for `queries` queries: heads [q][kHeadsLd], gthr [q], cnt [q], done [q].
+// All of it is zero between launches (the fused tail's last owner of a query clears what the query dirtied), so it
+// is zeroed once, when (re)allocated.
 size_t mma_state_bytes(int queries) {
-    return ((static_cast<size_t>(queries) * (kHeadsLd + 2) + static_cast<size_t>(queries) / kQ + 4) * sizeof(uint32_t) + 63) / 64 * 64;
+    return ((static_cast<size_t>(queries) * (kHeadsLd + 3) + 4) * sizeof(uint32_t) + 63) / 64 * 64;
 }
 
 int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* launches) {
@@ -119,10 +119,11 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
     // otherwise once, by k_prep_queries, and fetched by TMA: 128 live rows per CTA cost 25 us against 5 us.
     const bool fused_prep = q_resident && kblocks <= 8 && (split || (m.B <= 16 && !(split_launches & 1)));
     const bool fused_tail = m.k <= 64 && m.dump == nullptr && !(split_launches & 2);          // register-resident lists
-    // Eight epilogue warps pay when the score scan bounds the kernel (many live queries per tile); small batches are
-    // HBM-bound and run leaner with four.  (CODDVEC_K3_EW=4|8 forces one where both are built, k <= 16: A/B switch.)
+    // Epilogue warps: four (thread = query) by default; eight (two threads per query on alternate column chunks) are
+    // built for k <= 16 and selectable with CODDVEC_K3_EW=8.
     static const int ew_env = getenv("CODDVEC_K3_EW") ? atoi(getenv("CODDVEC_K3_EW")) : 0;
-    const int ew_pref = ew_env ? ew_env : (m.B <= 32 ? 4 : 8);
+    const int ew_pref = ew_env ? ew_env : 4;  // (same-box A/B, profiles/README.md: eight never beat four by more than noise once
+                                              //  the thresholds were tight; they stay selectable for k <= 16)
     const bool dump = m.dump != nullptr;
     MmaKernel kernel = cg == 2 ? pick_mma_kernel_cg2(dump, m.k, ew_pref) : pick_mma_kernel<1>(dump, m.k, ew_pref);
     const int ew = mma_kernel_epilogue_warps(dump, m.k, ew_pref);
@@ -165,7 +166,7 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
         uint32_t* heads = reinterpret_cast<uint32_t*>(scratch.state);                    // [state_q][kHeadsLd], 16-byte aligned rows
         uint32_t* gthr = heads + static_cast<size_t>(scratch.state_q) * kHeadsLd;         // [state_q]
         uint32_t* cnt = gthr + scratch.state_q;                                           // [state_q]
-        uint32_t* group_done = cnt + scratch.state_q;                                     // [state_q / kQ]
+        uint32_t* group_done = cnt + scratch.state_q;                                     // [state_q]
 
         CUtensorMap tq, te;
         memset(&tq, 0, sizeof(tq));
@@ -192,7 +193,8 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
         a.k = m.k;
         a.row_offset = m.row_offset;
         a.row_stride = m.row_stride ? m.row_stride : 1u;
-        a.scale_bounded = m.scale_bounded ? 1 : 0;
+        static const bool no_prefilter = getenv("CODDVEC_K3_NO_PREFILTER") != nullptr;  // A/B switch
+        a.scale_bounded = m.scale_bounded && !no_prefilter ? 1 : 0;
         a.n_tiles = n_tiles;
         a.q_tiles = QT;
         a.P = P;
@@ -210,6 +212,8 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
         a.cosine = m.cosine ? 1 : 0;
         a.split = split ? 1 : 0;
         a.fused_tail = fused_tail ? 1 : 0;
+        static const int exact_min_b = getenv("CODDVEC_K3_EXACT_HEADS_MIN_B") ? atoi(getenv("CODDVEC_K3_EXACT_HEADS_MIN_B")) : 64;
+        a.exact_heads = Bs >= exact_min_b ? 1 : 0;
         a.cand = lists;
         a.cand_ld = P * halves * m.k;
         a.cnt = cnt;
