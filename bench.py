@@ -74,7 +74,7 @@ def kernel_source_hash() -> str:
 
     h = hashlib.sha256()
     csrc = os.path.join(ROOT, "codd_query_engine_b200", "csrc")
-    for name in ("common.cuh", "k2_scan.cuh", "k3_mma.cu"):
+    for name in ("common.cuh", "k2_scan.cuh", "k3_kernel.cuh", "k3_mma.cu"):
         with open(os.path.join(csrc, name), "rb") as f:
             h.update(f.read())
     return h.hexdigest()[:16]
@@ -538,9 +538,13 @@ def sweep_small_configs(torch, native, D, k, pk):
             q = torch.randn((B, D), device="cuda", generator=gen)
             keys = torch.zeros((B, k), dtype=torch.int64, device="cuda")
             fn = lambda: idx.query_device(q.data_ptr(), B, k, keys.data_ptr(), stream=stream)  # noqa: E731
-            for _ in range(5):
-                fn()
-            torch.cuda.synchronize()
+            # warm up by TIME, not by count: the CPU baseline ran before this sweep with the GPU idle, and five
+            # 0.1 ms launches do not bring the clocks back up
+            t_warm = time.perf_counter()
+            while time.perf_counter() - t_warm < (0.5 if B == 1 else 0.1):
+                for _ in range(5):
+                    fn()
+                torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             iters = 30 if B <= 16 else 10
             e0.record()

@@ -39,9 +39,16 @@ def _deps_mtime() -> float:
     return max(f.stat().st_mtime for f in files)
 
 
-def _compile(unit: str, force: bool, checked: bool = False) -> Path:
+VARIANTS = {  # name -> (object directory, extra nvcc flags, library name)
+    "": ("obj", [], "libcoddvec.so"),
+    "checked": ("obj_checked", ["-DCV_CHECKED"], "libcoddvec_checked.so"),
+    "timeline": ("obj_timeline", ["-DCV_K3_TIMELINE"], "libcoddvec_timeline.so"),
+}
+
+
+def _compile(unit: str, force: bool, variant: str = "") -> Path:
     src = CSRC / unit
-    obj_dir = OBJ_DIR.parent / "obj_checked" if checked else OBJ_DIR
+    obj_dir = OBJ_DIR.parent / VARIANTS[variant][0]
     obj_dir.mkdir(parents=True, exist_ok=True)
     obj = obj_dir / (src.stem + ".o")
     log = obj_dir / (src.stem + ".ptxas.log")
@@ -52,7 +59,7 @@ def _compile(unit: str, force: bool, checked: bool = False) -> Path:
     env.pop("CC", None)
     env.pop("CXX", None)
     extra = os.environ.get("CODDVEC_NVCC_EXTRA", "").split()  # (-D switches of A/B experiment builds)
-    cmd = [_nvcc(), *NVCC_FLAGS, *(["-DCV_CHECKED"] if checked else []), *extra, "-ccbin", "/usr/bin/g++", "-c", str(src), "-o", str(obj)]
+    cmd = [_nvcc(), *NVCC_FLAGS, *VARIANTS[variant][1], *extra, "-ccbin", "/usr/bin/g++", "-c", str(src), "-o", str(obj)]
     proc = subprocess.run(cmd, capture_output=True, text=True, env=env)
     log.write_text(proc.stderr)
     if proc.returncode != 0:
@@ -60,14 +67,17 @@ def _compile(unit: str, force: bool, checked: bool = False) -> Path:
     return obj
 
 
-def build(force: bool = False, verbose: bool = False, checked: bool = False) -> Path:
-    """checked=True: libcoddvec_checked.so, the same sources with -DCV_CHECKED (device-side bounds assertions that
-    trap) -- select it with CODDVEC_LIB for the assertion pass that stands in for compute-sanitizer."""
+def build(force: bool = False, verbose: bool = False, checked: bool = False, variant: str = "") -> Path:
+    """variant "checked": libcoddvec_checked.so, the same sources with -DCV_CHECKED (device-side bounds assertions that
+    trap) -- the assertion pass that stands in for compute-sanitizer.  variant "timeline": libcoddvec_timeline.so with
+    -DCV_K3_TIMELINE (per-CTA phase stamps and a per-tile trace of K3, printed with CODDVEC_K3_TIMELINE=1 /
+    CODDVEC_K3_TRACE=1).  Select either with CODDVEC_LIB; the product library carries neither."""
+    variant = "checked" if checked else variant
     OBJ_DIR.mkdir(parents=True, exist_ok=True)
-    OUT = PKG / ("libcoddvec_checked.so" if checked else "libcoddvec.so")
+    OUT = PKG / VARIANTS[variant][2]
     units = [u for u in UNITS if (CSRC / u).exists()]
     with ThreadPoolExecutor(max_workers=min(len(units), os.cpu_count() or 4)) as pool:
-        objs = list(pool.map(lambda u: _compile(u, force, checked), units))
+        objs = list(pool.map(lambda u: _compile(u, force, variant), units))
     if force or not OUT.exists() or any(o.stat().st_mtime > OUT.stat().st_mtime for o in objs):
         env = dict(os.environ)
         env.pop("CC", None)
@@ -83,4 +93,5 @@ def build(force: bool = False, verbose: bool = False, checked: bool = False) -> 
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose=True, checked="--checked" in sys.argv)
+    build(force="--force" in sys.argv, verbose=True,
+          variant="checked" if "--checked" in sys.argv else ("timeline" if "--timeline" in sys.argv else ""))

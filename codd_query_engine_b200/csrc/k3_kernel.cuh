@@ -46,11 +46,16 @@ constexpr int kTN = 128;         // corpus rows per tile (UMMA N, TMEM columns p
 constexpr int kKB = 64;          // K elements per shared-memory block = 128 bytes = one swizzle row
 constexpr int kBlockBytes = kTN * kKB * 2;  // 16 KiB: one [128 rows][64] bf16 block (Q or corpus)
 constexpr int kMaxStages = 8;    // corpus ring depth: as many 16 KiB stages as fit next to the query tile (<= 8)
-constexpr int kAccStages = 2;
-constexpr int kThreads = 192;     // producer warp + MMA warp + 4 epilogue warps (EW = 4)
-constexpr int kThreadsWide = 320; // ... + 8 epilogue warps (EW = 8): two warps per TMEM lane quarter, alternate column chunks
+constexpr int kMaxAccStages = 4;
+// TMEM accumulator stages: all 512 columns either way -- four 128-column stages for single CTAs, two 256-column
+// stages for CTA pairs.  The stages are the slack between the MMA stream and the epilogue: a burst of list insertions
+// (every CTA's first tile) or a heads-bound refresh holds the epilogue for 5-8 us, and the HBM stream only keeps
+// running through it while the MMA issuer still has a free accumulator to write.
+__host__ __device__ constexpr int acc_stages(int cg) { return cg == 1 ? 4 : 2; }
+// threads per CTA: producer warp + MMA warp + EW epilogue warps (4, or 8: two warps per TMEM lane quarter on alternate
+// column chunks) + the bound warp
+__host__ __device__ constexpr int mma_threads(int ew) { return 96 + 32 * ew; }
 constexpr int kMaxKBlocks = 64;  // Dp <= 4096 (CV_MAX_DIM)
-constexpr uint32_t kTmemCols = kAccStages * kTN;  // 256
 
 constexpr int kHeadsLd = 320;    // >= max list owners per query (148 CTAs x 2 column halves), multiple of 4
 
@@ -85,7 +90,6 @@ struct KArgs {
     uint64_t corpus_hint;
     uint32_t row_stride;   // global row = row_offset + local row * row_stride (1 = dense block, G = cyclic shard)
     int scale_bounded;     // 1: every row scale is 0, NaN or within 2^-7 of 1 (enables the raw-dot prefilter)
-    int exact_heads;       // 1: in-scan threshold refreshes use the exact k-th largest head (large batches)
     // fused query preparation (q_resident only): the CTA normalises its 128 raw queries itself and writes the bf16
     // tile (and, with `split`, the bf16 residual tile) straight into the swizzled shared-memory layout
     const float* q_raw;    // [B][D] fp32 raw queries of this slice, or nullptr (the tile comes from tmap_q)
@@ -101,6 +105,7 @@ struct KArgs {
     uint32_t* done;        // [Bpad] list owners of the query that have published (the last one merges)
     uint64_t* out;         // [B][k] final keys of this slice
     unsigned long long* dbg;  // nullptr, or 4 words (atomicMax): prep ns, publish ns, merge ns, survivors per query
+    unsigned long long* tl;   // nullptr, or [gridDim.x][16] globaltimer stamps / wait totals of this CTA's phases (CODDVEC_K3_TIMELINE)
 };
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
@@ -281,104 +286,61 @@ __device__ __forceinline__ float shared_threshold(uint32_t g) {
     return ord_to_float(o);
 }
 
-// ---- cross-CTA "heads" bound (k <= 32) -----------------------------------------------------------------
-// Every CTA scanning rows for query q publishes the BEST score it has seen in heads[q][p] (a plain store to
-// its own slot, no atomics).  The k-th largest of those heads is a lower bound on the global k-th best score
-// (k different CTAs each hold a distinct row at least that good) and -- because the global top-k rows are
-// almost surely spread over different CTAs -- a tight one.  Each epilogue thread recomputes it for its query
-// at tiles 1, 4, 16, 64, ... of its CTA; after the first refresh a CTA only sees candidates that would
-// also beat the other CTAs' best rows, instead of converging its own lists from -inf
-// (k*ln(rows_per_cta/k) list updates per CTA and query).
-// The bound actually computed is slightly weaker but needs no arrays: the P slots are cut into k contiguous
-// groups and the bound is the SMALLEST group maximum (k distinct CTAs still each hold a row at least that
-// good).  Loads go out 8 x 16 bytes at a time.
-__device__ __forceinline__ uint32_t heads_bound(const uint32_t* row, int P, int k) {
-    if (P < k) return 0u;
-    uint32_t m = 0u, bound = 0xFFFFFFFFu;
-    int g = 0;
-    const int nv = (P + 3) / 4;
-    if (nv >= k) {  // group boundaries at 16-byte granularity
+// ---- cross-CTA "heads" bound (register lists, k <= 64) ----------------------------------------------------
+// Every list owner scanning rows for query q publishes the BEST score it has seen in heads[q][owner] (a plain store
+// to its own slot, once per tile).  The k-th largest of those heads is a lower bound on the global k-th best score
+// (k different owners each hold a distinct row at least that good) and -- because the global top-k rows are almost
+// surely spread over different CTAs -- a tight one.  It is computed by the bound warp of the query's duty CTA
+// (k_mma_topk) and travels to every owner through gthr[q].
+// Whole warp: the k-th LARGEST of the 32 * J values the lanes hold in v[] (destroyed), 0 if fewer than k are non-zero.
+// k rounds of "warp maximum, one holder drops one copy" -- ~20 instructions per round, no memory traffic.
+template <int J>
+__device__ __forceinline__ uint32_t warp_kth_largest(uint32_t (&v)[J], int k, int lane) {
+    uint32_t M = 0u;
 #pragma unroll 1
-        for (int v0 = 0; v0 < nv; v0 += 8) {
-            uint4 w[8];
+    for (int i = 0; i < k; ++i) {
+        uint32_t m = v[0];
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
-                w[u] = (v0 + u < nv) ? __ldcg(reinterpret_cast<const uint4*>(row) + v0 + u) : make_uint4(0u, 0u, 0u, 0u);
+        for (int j = 1; j < J; ++j) m = max(m, v[j]);
+        M = __reduce_max_sync(kFullMask, m);
+        if (M == 0u) return 0u;
+        const uint32_t holders = __ballot_sync(kFullMask, m == M);
+        if (lane == __ffs(holders) - 1) {
+            bool dropped = false;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                if (v0 + u < nv) {
-                    const int gv = (v0 + u) * k / nv;
-                    if (gv != g) { bound = min(bound, m); m = 0u; g = gv; }
-                    m = max(max(m, max(w[u].x, w[u].y)), max(w[u].z, w[u].w));
-                }
-            }
-        }
-    } else {  // few CTAs per query (pair mode, large batches): one slot at a time
-#pragma unroll 1
-        for (int s0 = 0; s0 < P; s0 += 8) {
-            uint32_t w[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) w[u] = (s0 + u < P) ? __ldcg(row + s0 + u) : 0u;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                if (s0 + u < P) {
-                    const int gv = (s0 + u) * k / P;
-                    if (gv != g) { bound = min(bound, m); m = 0u; g = gv; }
-                    m = max(m, w[u]);
-                }
+            for (int j = 0; j < J; ++j) {
+                const bool hit = !dropped && v[j] == M;
+                v[j] = hit ? 0u : v[j];
+                dropped |= hit;
             }
         }
     }
-    return min(bound, m);
+    return M;
 }
 
-// Exact version for short lists (KH <= 16 registers): the k-th LARGEST of the P heads.  At least k owners hold a row
-// that good, so it bounds the global k-th best from below -- and it is the tightest bound the heads give (the
-// grouped minimum above sits ~3x deeper in the ranking), which is what keeps the fused tail's survivor lists short.
-template <int KH>
-__device__ __forceinline__ uint32_t heads_kth(const uint32_t* row, int P, int k) {
-    if (P < k) return 0u;
-    uint32_t T[KH];  // right-aligned descending top-k; the slots before it are never-beaten sentinels
-#pragma unroll
-    for (int j = 0; j < KH; ++j) T[j] = (j < KH - k) ? 0xFFFFFFFFu : 0u;
-    const int nv = (P + 3) / 4;
-#pragma unroll 1
-    for (int v0 = 0; v0 < nv; v0 += 8) {
-        uint4 w[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-            w[u] = (v0 + u < nv) ? __ldcg(reinterpret_cast<const uint4*>(row) + v0 + u) : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const uint32_t x[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                if (x[e] > T[KH - 1]) {
-                    uint32_t cur = x[e];
-#pragma unroll
-                    for (int j = 0; j < KH; ++j) {
-                        const bool gt = cur > T[j];
-                        const uint32_t hi = gt ? cur : T[j];
-                        cur = gt ? T[j] : cur;
-                        T[j] = hi;
-                    }
-                }
-            }
-        }
-    }
-    return T[KH - 1];
-}
-
-// register-resident descending list: branch-free bubble insertion, no memory traffic
+// Register-resident descending list, no memory traffic.  Short lists insert by RANK: every slot compares the key with
+// its own and its left neighbour's old value (independent compares and selects, dependency depth ~4), where a bubble
+// pass chains KREG compare-exchanges (depth ~4 * KREG) -- and a lone epilogue warp has nothing to hide that latency
+// behind: every CTA's first tile is a burst of ~k * (1 + ln(128 / k)) insertions per query, 18 us with the bubble.
+// Long lists keep the bubble (the rank form needs old and new values live at once).
 template <int KREG>
 __device__ __forceinline__ void list_insert_regs(uint64_t (&L)[KREG], uint64_t key) {
-    uint64_t cur = key;
+    if (KREG <= 16) {
+        bool gt[KREG];
 #pragma unroll
-    for (int j = 0; j < KREG; ++j) {
-        const bool gt = cur > L[j];
-        const uint64_t hi = gt ? cur : L[j];
-        cur = gt ? L[j] : cur;
-        L[j] = hi;
+        for (int j = 0; j < KREG; ++j) gt[j] = key > L[j];  // monotone: false ... false true ... true
+#pragma unroll
+        for (int j = KREG - 1; j > 0; --j) L[j] = gt[j] ? (gt[j - 1] ? L[j - 1] : key) : L[j];
+        L[0] = gt[0] ? key : L[0];
+    } else {
+        uint64_t cur = key;
+#pragma unroll
+        for (int j = 0; j < KREG; ++j) {
+            const bool g = cur > L[j];
+            const uint64_t hi = g ? cur : L[j];
+            cur = g ? L[j] : cur;
+            L[j] = hi;
+        }
     }
 }
 
@@ -404,6 +366,9 @@ static __global__ void __launch_bounds__(128) k_prep_queries(const float* q, int
                                                       __nv_bfloat16* out) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+    // Programmatic dependent launch: k_mma_topk may start now (its prologue, tensor-map prefetch and first corpus
+    // loads do not depend on this kernel); it executes griddepcontrol.wait before it fetches the query tile.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (row >= Bpad) return;
     __nv_bfloat16* o = out + static_cast<size_t>(row) * Dp;
     if (row >= B) {
@@ -550,12 +515,13 @@ __device__ __forceinline__ void prep_query_tile(unsigned char* sm_q, const float
 //      w + 4 share a query and take alternate 32-column chunks of every tile, each with its own top-k list -- twice
 //      the issue slots and latency hiding for the score scan, which is what bounds large batches).
 template <bool DUMP, int KREG, int CG, int EW>
-__global__ void __launch_bounds__(64 + 32 * EW, 1)
+__global__ void __launch_bounds__(mma_threads(EW), 1)
 k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_e, const KArgs a) {
     constexpr int TN = kTN * CG;                       // corpus rows (= accumulator columns) per tile
     constexpr int kEpi = 32 * EW;                      // epilogue threads
     constexpr int kHalves = EW / 4;                    // list owners per (CTA, query)
-    constexpr uint32_t kCols = kAccStages * TN;        // TMEM columns: 256 (CG=1) / 512 (CG=2)
+    constexpr int kAccStages = acc_stages(CG);
+    constexpr uint32_t kCols = kAccStages * TN;        // TMEM columns: 512
     extern __shared__ __align__(1024) unsigned char smem[];
     // carve-up (all block bases 1024-byte aligned, as SWIZZLE_128B requires)
     // q_resident: [query tile: kblocks (x2 when split) x 16 KiB][ring: stages x 16 KiB corpus blocks]
@@ -568,23 +534,32 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
     unsigned char* sm_ring = smem + (qres ? static_cast<size_t>(qblocks) * kBlockBytes : 0);
     float* sm_scale = reinterpret_cast<float*>(sm_ring + static_cast<size_t>(kStages) * stage_bytes);  // [2][TN]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm_scale + kAccStages * TN);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1 + 2 * kAccStages);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1 + 2 * kMaxAccStages);
     uint64_t* sm_lists = reinterpret_cast<uint64_t*>(tmem_slot + 4);  // [128][k] when a.smem_lists
 
     const uint32_t bar_full = smem_u32(bars);                  // [kMaxStages] (leader's are the live ones)
     const uint32_t bar_empty = bar_full + 8 * kMaxStages;      // [kMaxStages]
     const uint32_t bar_q = bar_empty + 8 * kMaxStages;         // [1]
     const uint32_t bar_tfull = bar_q + 8;                      // [kAccStages]
-    const uint32_t bar_tempty = bar_tfull + 8 * kAccStages;    // [kAccStages] (leader's are the live ones)
+    const uint32_t bar_tempty = bar_tfull + 8 * kMaxAccStages; // [kAccStages] (leader's are the live ones)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    // (phase stamps exist only in the diagnostic build, -DCV_K3_TIMELINE: `tl` is a compile-time nullptr otherwise)
+#ifdef CV_K3_TIMELINE
+    unsigned long long* const tl = a.tl ? a.tl + static_cast<size_t>(blockIdx.x) * 16 : nullptr;
+#else
+    constexpr unsigned long long* tl = nullptr;
+#endif
+    if (tl && threadIdx.x == 0) tl[0] = global_timer_ns();     // 0: CTA entry
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;   // 0 = leader
     const int unit = blockIdx.x / CG;                         // CTA (CG=1) or CTA pair (CG=2)
     const int qt = unit % a.q_tiles;                          // query tile of 128*CG queries
     const int p = unit / a.q_tiles;
 
     if (threadIdx.x == 0) {
+        tmem_slot[1] = 0u;  // scan_done: the epilogue has scanned its last tile (-> bound warp)
+        tmem_slot[2] = 0u;  // bound_ack: the bound warp has published its last bound (-> epilogue, before the tail)
         for (int s = 0; s < kStages; ++s) {
             mbar_init(bar_full + 8 * s, CG);      // own arrive.expect_tx (+ the peer's remote arrive)
             mbar_init(bar_empty + 8 * s, 1);      // one tcgen05.commit
@@ -599,17 +574,16 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
     }
     if (warp == 1) tmem_alloc<CG>(smem_u32(tmem_slot), kCols);
     const bool fused_prep = a.q_raw != nullptr;  // (q_resident only)
-#ifndef CV_K3_NO_INKERNEL_PREP
     if (fused_prep) {
         const uint64_t t0 = a.dbg ? global_timer_ns() : 0;
-        prep_query_tile<64 + 32 * EW>(sm_q, a.q_raw, (qt * CG + static_cast<int>(rank)) * kQ, a.B, a.D, a.kblocks, a.cosine, a.split);
+        prep_query_tile<mma_threads(EW)>(sm_q, a.q_raw, (qt * CG + static_cast<int>(rank)) * kQ, a.B, a.D, a.kblocks, a.cosine, a.split);
         if (a.dbg && (threadIdx.x & 31) == 0) atomicMax(a.dbg, global_timer_ns() - t0);
     }
-#endif
     tc_fence_before();
     if (CG == 2) cluster_sync(); else __syncthreads();  // barriers, TMEM address and both CTAs' query tiles are ready
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (tl && threadIdx.x == 0) tl[1] = global_timer_ns();     // 1: prologue (barriers, TMEM, fused query prep) done
 
     if (warp == 0) {
         // ===================================================================== TMA producer (every CTA)
@@ -617,18 +591,27 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
             if (!fused_prep) tma_prefetch_desc(&tmap_q);
             tma_prefetch_desc(&tmap_e);
             const int q_row = (qt * CG + static_cast<int>(rank)) * kQ;
-            if (qres && !fused_prep) {
+            // The resident query tile comes from k_prep_queries, the previous launch in the stream.  This kernel is
+            // launched as its programmatic dependent, so everything up to here -- and the first ring-full of corpus
+            // blocks -- overlaps it; the tile itself is fetched after griddepcontrol.wait (prep complete and visible).
+            bool q_pending = qres && !fused_prep;
+            auto fetch_query_tile = [&]() {
+                asm volatile("griddepcontrol.wait;" ::: "memory");
                 const uint32_t q_bytes = static_cast<uint32_t>(a.kblocks) * kBlockBytes;
                 if (rank == 0) mbar_arrive_expect_tx(bar_q, q_bytes * CG);
                 else mbar_arrive_cluster(bar_q, 0);
                 for (int kb = 0; kb < a.kblocks; ++kb)
                     tma_load_2d<CG>(smem_u32(sm_q + static_cast<size_t>(kb) * kBlockBytes), &tmap_q, bar_q, kb * kKB, q_row,
                                     kEvictLast);
-            }
-            int stage = 0;
+                q_pending = false;
+            };
+            if (!qres && !fused_prep) asm volatile("griddepcontrol.wait;" ::: "memory");  // streamed query blocks ride in the ring
+            int stage = 0, issued = 0;
             uint32_t phase = 0;
             for (int t = p; t < a.n_tiles; t += a.P) {
                 for (int kb = 0; kb < a.kblocks; ++kb) {
+                    if (q_pending && issued == kStages) fetch_query_tile();  // the ring is full of requests: now the query tile
+                    ++issued;
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                     if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, stage_bytes * CG);
                     else mbar_arrive_cluster(bar_full + 8 * stage, 0);
@@ -642,6 +625,7 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
+            if (q_pending) fetch_query_tile();
         }
     } else if (warp == 1) {
         // ===================================================================== MMA issuer (leader CTA only)
@@ -653,13 +637,21 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
             }
             int stage = 0, as = 0;
             uint32_t phase = 0, aphase = 0;
+            uint64_t w_empty = 0, w_full = 0;  // (timeline only) ns spent waiting for the epilogue / for TMA data
             for (int t = p; t < a.n_tiles; t += a.P) {
+                const uint64_t tw0 = tl ? global_timer_ns() : 0;
                 mbar_wait(bar_tempty + 8 * as, aphase ^ 1);  // every epilogue warp has drained this accumulator stage
                 tc_fence_after();
+                const uint64_t tw1 = tl ? global_timer_ns() : 0;
+                w_empty += tw1 - tw0;
+                const int tidx = (t - p) / a.P;
+                unsigned long long* const tr = (tl && blockIdx.x == 0 && tidx < 64) ? a.tl + 16 * 296 + tidx * 6 : nullptr;
+                if (tr) { tr[0] = tw0; tr[1] = tw1; }
                 const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * TN);
                 for (int kb = 0; kb < a.kblocks; ++kb) {
                     mbar_wait(bar_full + 8 * stage, phase);  // TMA bytes of every CTA in the group have landed
                     tc_fence_after();
+                    if (tl && t == p && kb == 0) tl[2] = global_timer_ns();  // 2: first corpus block landed
                     const uint32_t slot = smem_u32(sm_ring + static_cast<size_t>(stage) * stage_bytes);
                     const uint32_t a_addr = qres ? smem_u32(sm_q + static_cast<size_t>(kb) * kBlockBytes) : slot;
                     const uint32_t b_addr = qres ? slot : slot + kBlockBytes;
@@ -678,9 +670,16 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
                 }
                 umma_commit<CG>(bar_tfull + 8 * as);  // accumulator complete -> epilogue warps (of both CTAs)
                 if (++as == kAccStages) { as = 0; aphase ^= 1; }
+                if (tl) w_full += global_timer_ns() - tw1;  // (issue time is negligible: this is the wait for TMA bytes)
+                if (tr) tr[2] = global_timer_ns();
+            }
+            if (tl) {
+                tl[3] = global_timer_ns();                     // 3: last MMA issued
+                tl[8] = w_empty;                               // 8: MMA issuer waited for a free accumulator (epilogue-bound)
+                tl[9] = w_full;                                // 9: MMA issuer waited for corpus blocks (HBM-bound)
             }
         }
-    } else {
+    } else if (warp < 2 + EW) {
         // ===================================================================== epilogue (32 * EW threads per CTA)
         const int et = threadIdx.x - 64;                 // 0 .. kEpi - 1
         const int half = (warp - 2) >> 2;                // which alternate column chunks this thread scans (EW = 8)
@@ -689,9 +688,6 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
         const int owner = half * a.P + p;                // this thread's slot among the lists / heads of its query
         const int owners = a.P * kHalves;
         CV_ASSERT(qglobal < a.Bpad && owner < owners && kHalves * ((a.P + 3) / 4 * 4) <= kHeadsLd && a.k <= (KREG > 0 ? KREG : kMaxK));
-        // (heads bound: a thread ranks the heads of its OWN column half only -- k distinct owners there still each
-        // hold a row at least that good, and the refresh costs what it does with four epilogue warps)
-        const uint32_t* const my_heads = a.heads + static_cast<size_t>(qglobal) * kHeadsLd + half * ((a.P + 3) / 4 * 4);
         const bool fused_tail = KREG > 0 && a.fused_tail != 0;
         uint64_t* const glist = fused_tail ? nullptr : a.lists + (static_cast<size_t>(owner) * a.Bpad + qglobal) * a.k;
         // large k (KREG == 0): the working list is in shared memory when it fits (fast warp-cooperative
@@ -741,8 +737,8 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
         constexpr int kScPer = (TN + kEpi - 1) / kEpi;   // tile rows whose scale each epilogue thread stages
         uint32_t* const head_row = a.heads + static_cast<size_t>(qglobal) * kHeadsLd;
         float best_local = -INFINITY;  // best score this thread has inserted (its head for this query)
-        int tcount = 0, next_refresh = 1;
-        const int my_tiles = (a.n_tiles - p + a.P - 1) / a.P;  // tiles this CTA processes
+        uint32_t g_pub = 0u;           // the last k-th best this thread published to gthr (ordered float)
+        int tcount = 0;
         float sc_next[kScPer];
 #pragma unroll
         for (int h = 0; h < kScPer; ++h) sc_next[h] = (h * kEpi + et < TN) ? row_scale(p, h * kEpi + et) : 0.0f;
@@ -750,41 +746,32 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
         auto fold_shared = [&](uint32_t g) {  // a lower bound on the global k-th best published by other list owners
             if (g > g_seen) { g_seen = g; thr = fmaxf(thr, shared_threshold(g)); }
         };
+        uint64_t e_top = 0, e_wait = 0, e_scan = 0;  // (timeline only) ns per phase of the epilogue loop, thread 0
         for (int t = p; t < a.n_tiles; t += a.P) {
+            const uint64_t te0 = tl ? global_timer_ns() : 0;
 #pragma unroll
             for (int h = 0; h < kScPer; ++h)
                 if (h * kEpi + et < TN) sm_scale[as * TN + h * kEpi + et] = sc_next[h];
             if (share) fold_shared(g_next);
-            if (KREG > 0 && share) {
-                // heads bound at tiles 1, 4, 16, 64, ... of this CTA and once more before its last tile (the fused
-                // tail publishes the keys above the bound folded in by then)
-#ifdef CV_K3_NO_LAST_REFRESH
-                const bool last = false;
-#else
-                const bool last = tcount + 1 == my_tiles && my_tiles > 2;
-#endif
-                if (tcount == next_refresh || last) {
-                    // The exact k-th largest head costs ~7 us of this thread's time.  Before the last tile it always
-                    // pays (it decides how many keys the fused tail has to merge).  During the scan it pays when
-                    // candidate handling bounds the kernel -- large batches: a tight bound early spares every CTA
-                    // most of its list convergence (B = 256 at 1M rows: 0.24 -> 0.20 ms) -- and costs 5 % when the
-                    // scan is HBM-bound, where the cheap grouped bound is used instead.
-                    const bool exact = KREG <= 16 && (last || a.exact_heads != 0);
-                    if (last || tcount * 8 <= my_tiles)
-                        fold_shared(exact ? heads_kth<KR>(my_heads, a.P, a.k) : heads_bound(my_heads, a.P, a.k));
-                    if (tcount == next_refresh) next_refresh *= 4;
-                }
-            }
             ++tcount;
             // prefetch for the next tile of this CTA (in flight while this tile is processed)
 #pragma unroll
             for (int h = 0; h < kScPer; ++h) sc_next[h] = (h * kEpi + et < TN) ? row_scale(t + a.P, h * kEpi + et) : 0.0f;
             if (share) g_next = __ldcg(a.gthr + qglobal);
             asm volatile("bar.sync 1, %0;" ::"n"(kEpi) : "memory");  // this CTA's epilogue warps only
+            const uint64_t te1 = tl ? global_timer_ns() : 0;
             mbar_wait(bar_tfull + 8 * as, aphase);
             tc_fence_after();
+            const uint64_t te2 = tl ? global_timer_ns() : 0;
+            if (tl && et == 0 && t == p) tl[4] = te2;          // 4: first accumulator ready
             const float* sc_tile = sm_scale + as * TN;
             const uint32_t lrow0 = static_cast<uint32_t>(t) * TN;  // local row of the tile's first column
+            // Cross-CTA publications happen ONCE per tile, after its scan: in every CTA's first tiles each inserted
+            // candidate used to raise the query's shared k-th best (a RED) and this owner's head (a store) -- 148 CTAs
+            // x dozens of same-address reductions per query at the same moment.  L2 serialises those, the SM's memory
+            // queue backs up behind them, and the mbarrier traffic of the pipeline (shared memory, same queue) waits
+            // with it: 20-30 us per batch at 1M rows (per-tile trace, profiles/README.md).
+            bool tile_changed = false, head_changed = false;
 #pragma unroll 1
             for (int c = half; c < TN / 32; c += kHalves) {
                 uint32_t v[32];
@@ -828,7 +815,6 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
                         uint32_t cand = 0;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) cand |= (__uint_as_float(v[j]) > thr) ? (1u << j) : 0u;
-                        bool changed = false;
                         while (cand) {
                             const int j = __ffs(cand) - 1;
                             cand &= cand - 1;
@@ -837,14 +823,13 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
                                 list_insert_regs<KR>(L, pack_key(s, a.row_offset + (lrow0 + c * 32 + j) * a.row_stride));
                                 if (L[KR - 1] != 0ull) thr_local = key_score(L[KR - 1]);
                                 thr = fmaxf(thr, thr_local);
-                                if (share && s > best_local) {  // publish this owner's new head for the query
+                                if (s > best_local) {
                                     best_local = s;
-                                    __stcg(head_row + half * ((a.P + 3) / 4 * 4) + p, ord_of(s));
+                                    head_changed = true;
                                 }
-                                changed = true;
+                                tile_changed = true;
                             }
                         }
-                        if (changed && share && L[KR - 1] != 0ull) red_max_u32(a.gthr + qglobal, ord_of(thr_local));
                     }
                 } else if (__any_sync(kFullMask, any)) {
                     // large k: the lists live in global memory (L1/L2 resident) and the whole warp inserts
@@ -876,7 +861,10 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
                         if (lane == src && changed) {
                             thr_local = local_src;
                             thr = thr_src;
-                            if (share && local_src > -INFINITY) red_max_u32(a.gthr + qglobal, ord_of(local_src));
+                            if (share && local_src > -INFINITY && ord_of(local_src) > max(g_seen, g_pub)) {
+                                g_pub = ord_of(local_src);
+                                red_max_u32(a.gthr + qglobal, g_pub);
+                            }
                         }
                     }
                 }
@@ -887,7 +875,39 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
                 if (rank == 0) mbar_arrive(bar_tempty + 8 * as);
                 else mbar_arrive_cluster(bar_tempty + 8 * as, 0);
             }
+            if (KREG > 0 && share) {
+                // this owner's new head for the query, and its k-th best if that can still raise the shared bound (once
+                // the heads bound is folded in, a single owner's k-th best almost never can)
+                if (head_changed) __stcg(head_row + half * ((a.P + 3) / 4 * 4) + p, ord_of(best_local));
+                if (tile_changed && L[KR - 1] != 0ull) {
+                    const uint32_t o = ord_of(thr_local);
+                    if (o > max(g_seen, g_pub)) {
+                        g_pub = o;
+                        red_max_u32(a.gthr + qglobal, o);
+                    }
+                }
+            }
             if (++as == kAccStages) { as = 0; aphase ^= 1; }
+            if (tl) {
+                const uint64_t te3 = global_timer_ns();
+                e_top += te1 - te0;
+                e_wait += te2 - te1;
+                e_scan += te3 - te2;
+                if (blockIdx.x == 0 && et == 0 && tcount <= 64) {
+                    unsigned long long* const tr = a.tl + 16 * 296 + (tcount - 1) * 6;
+                    tr[3] = te1; tr[4] = te2; tr[5] = te3;
+                }
+            }
+        }
+        // the bound warp stops publishing before any owner reports "done" (the last owner of a query resets gthr)
+        if (et == 0) *reinterpret_cast<volatile uint32_t*>(tmem_slot + 1) = 1u;
+        if (fused_tail && owners > 1)
+            while (*reinterpret_cast<volatile uint32_t*>(tmem_slot + 2) == 0u) {}
+        if (tl && et == 0) {
+            tl[5] = global_timer_ns();                          // 5: last tile scanned
+            tl[10] = e_top;                                     // 10: epilogue loop top (scales, bounds, refreshes, bar.sync)
+            tl[11] = e_wait;                                    // 11: epilogue waited for an accumulator (it was ahead)
+            tl[12] = e_scan;                                    // 12: TMEM loads + score scan + insertions
         }
         if (fused_tail) {
             // ---- fused tail: no merge launch.  A single list owner: its list is final.  Otherwise every owner
@@ -963,13 +983,59 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
             __syncwarp();
             for (int j = 0; j < a.k; ++j) glist[j] = list[j];
         }
+    } else {
+        // ===================================================================== bound warp
+        // Keeps the shared lower bound of the global k-th best fresh WITHOUT the epilogue's help.  Every list owner
+        // publishes its best score per query (its "head"); the k-th largest head bounds the global k-th best from
+        // below (k distinct owners each hold a row at least that good) and, unlike one owner's own k-th best, reflects
+        // every row the grid has scanned.  Each query has ONE duty CTA (p == query % P): its bound warp re-reads the
+        // query's heads row over and over (coalesced, one L2 round trip), ranks it with warp reductions and raises
+        // gthr[q], which every epilogue thread reads once per tile anyway.  (When the epilogue threads ranked the heads
+        // themselves -- all 148 CTAs x 128 threads at the same tiles -- the loads queued in L2 and each refresh held
+        // the scan for 10-30 us: per-tile trace, profiles/README.md.)
+        volatile uint32_t* const scan_done = tmem_slot + 1;
+        volatile uint32_t* const bound_ack = tmem_slot + 2;
+        constexpr int J = 5;                               // 32 * J >= P (at most 148 list owners per column half)
+        const int Pr = (a.P + 3) / 4 * 4;
+        const int q0 = (qt * CG + static_cast<int>(rank)) * kQ;
+        if (KREG > 0 && !DUMP && a.P >= a.k && a.P <= 32 * J && p < kQ && q0 + p < a.B) {
+            bool dirty = false;  // a RED has been issued since the last fence
+            while (*scan_done == 0u) {
+                if (dirty) {  // (REDs are rare once the heads have settled: no fence in the steady state)
+                    __threadfence();
+                    dirty = false;
+                }
+                for (int ql = p; ql < kQ && q0 + ql < a.B && *scan_done == 0u; ql += a.P) {
+                    const int qg = q0 + ql;
+#pragma unroll 1
+                    for (int h = 0; h < kHalves; ++h) {
+                        const uint32_t* row = a.heads + static_cast<size_t>(qg) * kHeadsLd + h * Pr;
+                        uint32_t v[J];
+#pragma unroll
+                        for (int j = 0; j < J; ++j) v[j] = (lane + 32 * j < a.P) ? __ldcg(row + lane + 32 * j) : 0u;
+                        const uint32_t cur = __ldcg(a.gthr + qg);
+                        const uint32_t kth = warp_kth_largest<J>(v, a.k, lane);
+                        if (kth > cur && *scan_done == 0u) {  // (warp-uniform)
+                            if (lane == 0) red_max_u32(a.gthr + qg, kth);
+                            dirty = true;
+                        }
+                    }
+                }
+                __nanosleep(200);
+            }
+            if (dirty) __threadfence();  // every RED above is visible before the ack below can be
+        }
+        __syncwarp();
+        if (lane == 0) *bound_ack = 1u;
     }
+    if (tl && threadIdx.x == 64) tl[6] = global_timer_ns();    // 6: tail (publish / merge / list write-out) done
     tc_fence_before();
     if (CG == 2) cluster_sync(); else __syncthreads();  // nobody leaves while its partner may still touch it
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc<CG>(tmem_base, kCols);
     }
+    if (tl && threadIdx.x == 32) tl[7] = global_timer_ns();    // 7: CTA exit
 }
 
 using MmaKernel = void (*)(const CUtensorMap, const CUtensorMap, const KArgs);
@@ -979,9 +1045,7 @@ using MmaKernel = void (*)(const CUtensorMap, const CUtensorMap, const KArgs);
 template <int CG>
 inline MmaKernel pick_mma_kernel(bool dump, int k, int ew) {
     if (dump) return k_mma_topk<true, 0, CG, 4>;
-#ifndef CV_K3_NO_KREG10
     if (k <= 10) return ew == 4 ? static_cast<MmaKernel>(k_mma_topk<false, 10, CG, 4>) : static_cast<MmaKernel>(k_mma_topk<false, 10, CG, 8>);
-#endif
     if (k <= 16) return ew == 4 ? static_cast<MmaKernel>(k_mma_topk<false, 16, CG, 4>) : static_cast<MmaKernel>(k_mma_topk<false, 16, CG, 8>);
     if (k <= 32) return k_mma_topk<false, 32, CG, 4>;
     if (k <= 64) return k_mma_topk<false, 64, CG, 4>;

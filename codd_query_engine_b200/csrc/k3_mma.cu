@@ -1,5 +1,7 @@
 // k3_mma.cu -- host side of K3 `gemm_topk` (kernel: k3_kernel.cuh): shapes, scratch, tensor maps, launches.
 #include "k3_kernel.cuh"
+#include <algorithm>
+#include <vector>
 
 namespace cv {
 
@@ -12,8 +14,8 @@ constexpr size_t kSmemLimit = 232448;  // 227 KiB: the per-CTA maximum on sm_100
 // qblocks: 16 KiB blocks of the resident query tile (0 when the tile is streamed through the ring)
 size_t mma_smem_bytes(int qblocks, int stages, int cg, size_t list_bytes, bool q_resident) {
     const size_t blocks = q_resident ? static_cast<size_t>(qblocks + stages) : 2 * static_cast<size_t>(stages);
-    return blocks * kBlockBytes + kAccStages * kTN * cg * sizeof(float) +
-           (2 * kMaxStages + 1 + 2 * kAccStages) * sizeof(uint64_t) + 16 + list_bytes;
+    return blocks * kBlockBytes + acc_stages(cg) * kTN * cg * sizeof(float) +
+           (2 * kMaxStages + 1 + 2 * kMaxAccStages) * sizeof(uint64_t) + 16 + list_bytes;
 }
 
 int mma_stages(int qblocks, int cg, size_t list_bytes, bool q_resident) {
@@ -75,6 +77,8 @@ int raise_smem_limit(MmaKernel kernel) {
 // Self-resetting cross-CTA state for `queries` queries: heads [q][kHeadsLd], gthr [q], cnt [q], done [q].
 // All of it is zero between launches (the fused tail's last owner of a query clears what the query dirtied), so it
 // is zeroed once, when (re)allocated.
+constexpr size_t kDebugBytes = 64 + (296 * 16 + 64 * 6) * sizeof(unsigned long long);  // CODDVEC_K3_DEBUG words + CODDVEC_K3_TIMELINE stamps
+
 size_t mma_state_bytes(int queries) {
     return ((static_cast<size_t>(queries) * (kHeadsLd + 3) + 4) * sizeof(uint32_t) + 63) / 64 * 64;
 }
@@ -117,7 +121,8 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
     // The query tile is built inside the kernel when that is cheap -- up to 16 queries (every CTA normalises them
     // again, ~0.4 us per query) or short rows (the hi/lo split's second tile only exists in shared memory) --
     // otherwise once, by k_prep_queries, and fetched by TMA: 128 live rows per CTA cost 25 us against 5 us.
-    const bool fused_prep = q_resident && kblocks <= 8 && (split || (m.B <= 16 && !(split_launches & 1)));
+    static const int fused_prep_max_b = getenv("CODDVEC_K3_FUSED_PREP_MAX_B") ? atoi(getenv("CODDVEC_K3_FUSED_PREP_MAX_B")) : 0;
+    const bool fused_prep = q_resident && kblocks <= 8 && (split || (m.B <= fused_prep_max_b && !(split_launches & 1)));
     const bool fused_tail = m.k <= 64 && m.dump == nullptr && !(split_launches & 2);          // register-resident lists
     // Epilogue warps: four (thread = query) by default; eight (two threads per query on alternate column chunks) are
     // built for k <= 16 and selectable with CODDVEC_K3_EW=8.
@@ -157,8 +162,8 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
             scratch.state = nullptr;
             scratch.state_q = 0;
             const int cap_q = std::max(Bpad, 1024);
-            MMA_CUDA(cudaMalloc(&scratch.state, mma_state_bytes(cap_q) + 64));  // (+ 8 debug words)
-            MMA_CUDA(cudaMemsetAsync(scratch.state, 0, mma_state_bytes(cap_q) + 64, m.stream));
+            MMA_CUDA(cudaMalloc(&scratch.state, mma_state_bytes(cap_q) + kDebugBytes));  // (+ debug words, timeline)
+            MMA_CUDA(cudaMemsetAsync(scratch.state, 0, mma_state_bytes(cap_q) + kDebugBytes, m.stream));
             scratch.state_q = cap_q;
         }
         __nv_bfloat16* qb = reinterpret_cast<__nv_bfloat16*>(scratch.p);
@@ -212,8 +217,6 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
         a.cosine = m.cosine ? 1 : 0;
         a.split = split ? 1 : 0;
         a.fused_tail = fused_tail ? 1 : 0;
-        static const int exact_min_b = getenv("CODDVEC_K3_EXACT_HEADS_MIN_B") ? atoi(getenv("CODDVEC_K3_EXACT_HEADS_MIN_B")) : 64;
-        a.exact_heads = Bs >= exact_min_b ? 1 : 0;
         a.cand = lists;
         a.cand_ld = P * halves * m.k;
         a.cnt = cnt;
@@ -221,19 +224,33 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
         a.out = m.out + static_cast<size_t>(done) * m.k;
         static const bool debug = getenv("CODDVEC_K3_DEBUG") != nullptr;
         a.dbg = debug ? reinterpret_cast<unsigned long long*>(scratch.state + mma_state_bytes(scratch.state_q)) : nullptr;
+#ifdef CV_K3_TIMELINE
+        static const bool timeline = getenv("CODDVEC_K3_TIMELINE") != nullptr;
+#else
+        static const bool timeline = false;  // (python -m codd_query_engine_b200.build --timeline builds the diagnostic library)
+#endif
+        a.tl = timeline ? reinterpret_cast<unsigned long long*>(scratch.state + mma_state_bytes(scratch.state_q) + 64) : nullptr;
 
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(static_cast<unsigned>(QT * P * cg));
-        cfg.blockDim = dim3(static_cast<unsigned>(64 + 32 * ew));
+        cfg.blockDim = dim3(static_cast<unsigned>(mma_threads(ew)));
         cfg.dynamicSmemBytes = smem;
         cfg.stream = m.stream;
-        cudaLaunchAttribute attr[1];
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = static_cast<unsigned>(cg);
         attr[0].val.clusterDim.y = 1;
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
+        // after k_prep_queries: programmatic dependent launch -- this kernel's prologue and first corpus loads overlap
+        // the query preparation (the kernel waits with griddepcontrol.wait before it touches the prepared tile)
+        static const bool no_pdl = getenv("CODDVEC_K3_PDL") && atoi(getenv("CODDVEC_K3_PDL")) == 0;  // A/B switch
+        if (!fused_prep && !no_pdl) {
+            attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[1].val.programmaticStreamSerializationAllowed = 1;
+            cfg.numAttrs = 2;
+        }
         MMA_CUDA(cudaLaunchKernelEx(&cfg, kernel, tq, te, a));
         if (launches) launches->fetch_add(1);
         if (!fused_tail) {
@@ -245,6 +262,36 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
             if (launches) launches->fetch_add(1);
         }
         done += Bs;
+        if (a.tl) {  // CODDVEC_K3_TIMELINE: per-CTA phase stamps (synchronises; never set in production)
+            const int ctas = QT * P * cg;
+            std::vector<unsigned long long> w(static_cast<size_t>(ctas) * 16);
+            MMA_CUDA(cudaStreamSynchronize(m.stream));
+            MMA_CUDA(cudaMemcpy(w.data(), a.tl, w.size() * 8, cudaMemcpyDeviceToHost));
+            unsigned long long t0 = ~0ull;
+            for (int c = 0; c < ctas; ++c) t0 = std::min(t0, w[c * 16]);
+            static const char* names[13] = {"entry", "prologue", "first block", "last mma", "first acc", "last scan", "tail", "exit",
+                                            "mma: wait acc", "mma: wait tma", "epi: loop top", "epi: wait acc", "epi: scan"};
+            fprintf(stderr, "[k3 timeline] B=%d cg=%d P=%d tiles/cta=%.1f (us after the first CTA's entry: min / median / max)\n", Bs, cg, P,
+                    static_cast<double>(n_tiles) / P);
+            for (int e = 0; e < 13; ++e) {
+                std::vector<double> v;
+                for (int c = 0; c < ctas; ++c)
+                    if (w[c * 16 + e]) v.push_back((w[c * 16 + e] - (e < 8 ? t0 : 0ull)) * 1e-3);
+                if (v.empty()) continue;
+                std::sort(v.begin(), v.end());
+                fprintf(stderr, "[k3 timeline]   %-14s %8.1f %8.1f %8.1f\n", names[e], v.front(), v[v.size() / 2], v.back());
+            }
+            static const bool trace = getenv("CODDVEC_K3_TRACE") != nullptr;
+            if (trace) {  // CTA 0, tile by tile: MMA issuer (asks for acc, has acc, tile committed), epilogue (asks, has acc, done)
+                std::vector<unsigned long long> tr(64 * 6);
+                MMA_CUDA(cudaMemcpy(tr.data(), a.tl + 16 * 296, tr.size() * 8, cudaMemcpyDeviceToHost));
+                for (int i = 0; i < 64 && tr[i * 6]; ++i)
+                    fprintf(stderr, "[k3 trace] tile %2d  mma ask %7.2f got %7.2f committed %7.2f | epi ask %7.2f got %7.2f done %7.2f\n", i,
+                            (tr[i * 6] - t0) * 1e-3, (tr[i * 6 + 1] - t0) * 1e-3, (tr[i * 6 + 2] - t0) * 1e-3, (tr[i * 6 + 3] - t0) * 1e-3,
+                            (tr[i * 6 + 4] - t0) * 1e-3, (tr[i * 6 + 5] - t0) * 1e-3);
+            }
+            MMA_CUDA(cudaMemset(a.tl, 0, (296 * 16 + 64 * 6) * 8));
+        }
         if (a.dbg) {  // CODDVEC_K3_DEBUG: in-kernel timers of the fused phases (synchronises; never set in production)
             unsigned long long w[4] = {0, 0, 0, 0};
             MMA_CUDA(cudaStreamSynchronize(m.stream));
