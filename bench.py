@@ -68,13 +68,19 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
-def kernel_source_hash() -> str:
-    """sha256 over the CUDA sources of the query kernels: stamps an ncu capture with the code it measured."""
+KERNEL_SOURCES = {"k_scan_topk": ("common.cuh", "k2_scan.cuh"),
+                  "k_mma_topk": ("common.cuh", "k3_kernel.cuh", "k3_mma.cu")}
+
+
+def kernel_source_hash(kernel: str = "") -> str:
+    """sha256 over the CUDA sources of one query kernel (all of them for ""): stamps an ncu capture with the code it
+    measured."""
     import hashlib
 
     h = hashlib.sha256()
     csrc = os.path.join(ROOT, "codd_query_engine_b200", "csrc")
-    for name in ("common.cuh", "k2_scan.cuh", "k3_kernel.cuh", "k3_mma.cu"):
+    names = KERNEL_SOURCES[kernel] if kernel else sorted({n for v in KERNEL_SOURCES.values() for n in v})
+    for name in names:
         with open(os.path.join(csrc, name), "rb") as f:
             h.update(f.read())
     return h.hexdigest()[:16]
@@ -93,7 +99,7 @@ def traffic_for(kernel: str, rows: int, dim: int, batch: int):
     t = doc.get(kernel)
     if not t or t.get("dim") != dim or t.get("batch") != batch:
         return None, "no ncu capture of this kernel at this dim / batch"
-    have = kernel_source_hash()
+    have = kernel_source_hash(kernel)
     if t.get("kernel_source_hash") != have:
         return None, f"ncu capture is of kernel sources {t.get('kernel_source_hash')}, this run executes {have}: not reported"
     return float(t["bytes_per_launch"]) * (rows / float(t["rows"])), f"{t.get('source')} (kernel sources {have}), scaled by rows"
@@ -449,6 +455,14 @@ def run_ours(args):
     pk = peaks()
     big = 0 if args.no_batch_leg or B >= args.batch_leg else args.batch_leg
 
+    # BASELINE configs[1] first, on a GPU that has not yet been driven into its power cap by the 100M-row legs (the
+    # batch-1024 leg holds the SM clock near 1.25 GHz for seconds; small-corpus K3 batches are clock-sensitive)
+    configs, configs_clocks = None, None
+    if rank == 0 and world == 1 and not args.no_extras:
+        with ClockSampler(local_rank) as clk_cfg:
+            configs = sweep_small_configs(torch, native, D, k, pk)
+        configs_clocks = clk_cfg.summary()
+
     t_build = time.perf_counter()
     index = ShardedIndex(D, args.rows, device=device, exchange=args.exchange, max_queries=max(B, big, 1), max_k=max(k, 1))
     build_shard(index, index.lo, index.hi, D, torch, device)
@@ -487,8 +501,9 @@ def run_ours(args):
 
     if rank == 0 and world == 1 and not args.no_extras:
         line["cpu_baseline"] = cpu_baseline(args, index, q_host)
-        index.close()  # free the corpus before the small-config sweep builds its own
-        line["configs"] = sweep_small_configs(torch, native, D, k, pk)
+        index.close()
+        line["configs"] = configs
+        line["configs_clocks"] = configs_clocks
         line["reference_case"] = reference_case(torch, native, D, k)
     else:
         index.close()
@@ -538,15 +553,14 @@ def sweep_small_configs(torch, native, D, k, pk):
             q = torch.randn((B, D), device="cuda", generator=gen)
             keys = torch.zeros((B, k), dtype=torch.int64, device="cuda")
             fn = lambda: idx.query_device(q.data_ptr(), B, k, keys.data_ptr(), stream=stream)  # noqa: E731
-            # warm up by TIME, not by count: the CPU baseline ran before this sweep with the GPU idle, and five
-            # 0.1 ms launches do not bring the clocks back up
+            # warm up by TIME, not by count: five 0.1 ms launches do not bring an idle GPU's clocks up
             t_warm = time.perf_counter()
             while time.perf_counter() - t_warm < (0.5 if B == 1 else 0.1):
                 for _ in range(5):
                     fn()
                 torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            iters = 30 if B <= 16 else 10
+            iters = 100 if B <= 256 else 30
             e0.record()
             for _ in range(iters):
                 fn()

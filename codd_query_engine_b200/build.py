@@ -24,7 +24,7 @@ NVCC_FLAGS = [
     "-Xptxas", "-v",
     "-diag-suppress", "177",
 ]
-UNITS = ["coddvec.cu", "k2_inst_qb1.cu", "k2_inst_qb2.cu", "k2_inst_qb4.cu", "k3_mma.cu", "k3_inst_cg2.cu"]
+UNITS = ["coddvec.cu", "k2_inst_qb1.cu", "k2_inst_qb2.cu", "k2_inst_qb4.cu", "k3_mma.cu", "k3_inst_cg2.cu", "k3_inst_pilot.cu"]
 
 
 def _nvcc() -> str:

@@ -514,7 +514,10 @@ __device__ __forceinline__ void prep_query_tile(unsigned char* sm_q, const float
 // EW = epilogue warps: 4 (one per TMEM lane quarter; thread = query) or 8 (two per quarter: the threads of warps w and
 //      w + 4 share a query and take alternate 32-column chunks of every tile, each with its own top-k list -- twice
 //      the issue slots and latency hiding for the score scan, which is what bounds large batches).
-template <bool DUMP, int KREG, int CG, int EW>
+// PILOT = two-pass first tile (see the epilogue): its own instantiations, so that the kernels that do not use it --
+//      CTA pairs, long scans -- keep exactly the code they had (the mere presence of the branch in the tile loop cost
+//      them 2-5 % in same-box A/B runs).
+template <bool DUMP, int KREG, int CG, int EW, bool PILOT = false>
 __global__ void __launch_bounds__(mma_threads(EW), 1)
 k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_e, const KArgs a) {
     constexpr int TN = kTN * CG;                       // corpus rows (= accumulator columns) per tile
@@ -766,11 +769,40 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
             if (tl && et == 0 && t == p) tl[4] = te2;          // 4: first accumulator ready
             const float* sc_tile = sm_scale + as * TN;
             const uint32_t lrow0 = static_cast<uint32_t>(t) * TN;  // local row of the tile's first column
-            // Cross-CTA publications happen ONCE per tile, after its scan: in every CTA's first tiles each inserted
-            // candidate used to raise the query's shared k-th best (a RED) and this owner's head (a store) -- 148 CTAs
-            // x dozens of same-address reductions per query at the same moment.  L2 serialises those, the SM's memory
-            // queue backs up behind them, and the mbarrier traffic of the pipeline (shared memory, same queue) waits
-            // with it: 20-30 us per batch at 1M rows (per-tile trace, profiles/README.md).
+            // ---- pilot (first tile only): every CTA starts with empty lists, and converging a list from -inf costs
+            // ~k * (1 + ln(columns / k)) insertions per query -- one warp per 32 queries, ~0.25 us per warp-wide
+            // insertion round: 18 us on a 128-column tile, 26 us on a 256-column one (per-tile trace,
+            // profiles/README.md), far beyond what the accumulator stages can hide.  So the first tile is read twice.
+            // Pass A only takes each query's maximum over the tile and publishes it as this owner's head; the duty
+            // CTA's bound warp answers with the k-th largest of ALL owners' first heads (rank ~k among P x 128 rows
+            // instead of among 128); pass B is the normal scan under that bound and inserts almost nothing.  The wait
+            // (~3 us: two L2 round trips on either side) is bounded, and the MMA issuer keeps the stream running into
+            // the free accumulator stages meanwhile.
+            if (PILOT && KREG > 0 && !DUMP && tcount == 1 && owners > 1) {  // (warp-uniform: tcgen05.ld is collective)
+                float mx = -INFINITY;
+#pragma unroll 1
+                for (int c = half; c < TN / 32; c += kHalves) {
+                    uint32_t v[32];
+                    tmem_ld32(lane_base + static_cast<uint32_t>(as * TN + c * 32), v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]) * sc_tile[c * 32 + j]);  // (NaN = skip)
+                }
+                if (share) {
+                    best_local = mx;
+                    __stcg(head_row + half * ((a.P + 3) / 4 * 4) + p, ord_of(mx));
+                    uint32_t g = 0u;
+#pragma unroll 1
+                    for (int tries = 0; tries < 12 && g == 0u; ++tries) {
+                        if (tries) __nanosleep(250);
+                        g = __ldcg(a.gthr + qglobal);
+                    }
+                    fold_shared(g);
+                }
+                __syncwarp();
+            }
+            // Cross-CTA publications happen ONCE per tile, after its scan (this owner's head if it rose, its k-th best
+            // if that can still raise the shared bound): a store and at most one RED per query and tile.
             bool tile_changed = false, head_changed = false;
 #pragma unroll 1
             for (int c = half; c < TN / 32; c += kHalves) {
@@ -1000,6 +1032,7 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
         const int q0 = (qt * CG + static_cast<int>(rank)) * kQ;
         if (KREG > 0 && !DUMP && a.P >= a.k && a.P <= 32 * J && p < kQ && q0 + p < a.B) {
             bool dirty = false;  // a RED has been issued since the last fence
+            int passes = 0;      // pilot: the first bound of a query is taken over EVERY owner's first head (or after ~8 us)
             while (*scan_done == 0u) {
                 if (dirty) {  // (REDs are rare once the heads have settled: no fence in the steady state)
                     __threadfence();
@@ -1014,6 +1047,10 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
 #pragma unroll
                         for (int j = 0; j < J; ++j) v[j] = (lane + 32 * j < a.P) ? __ldcg(row + lane + 32 * j) : 0u;
                         const uint32_t cur = __ldcg(a.gthr + qg);
+                        bool all_in = true;
+#pragma unroll
+                        for (int j = 0; j < J; ++j) all_in &= (lane + 32 * j >= a.P) || v[j] != 0u;
+                        if (PILOT && passes < 8 && !__all_sync(kFullMask, all_in)) continue;
                         const uint32_t kth = warp_kth_largest<J>(v, a.k, lane);
                         if (kth > cur && *scan_done == 0u) {  // (warp-uniform)
                             if (lane == 0) red_max_u32(a.gthr + qg, kth);
@@ -1021,6 +1058,7 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
                         }
                     }
                 }
+                ++passes;
                 __nanosleep(200);
             }
             if (dirty) __threadfence();  // every RED above is visible before the ack below can be
@@ -1054,6 +1092,8 @@ inline MmaKernel pick_mma_kernel(bool dump, int k, int ew) {
 inline int mma_kernel_epilogue_warps(bool dump, int k, int ew) { return (!dump && k <= 16 && ew == 8) ? 8 : 4; }
 
 MmaKernel pick_mma_kernel_cg2(bool dump, int k, int ew);  // k3_inst_cg2.cu
+// PILOT instantiations (two-pass first tile; single CTAs, four epilogue warps, register lists): k3_inst_pilot.cu
+MmaKernel pick_mma_kernel_pilot(int k);
 
 }  // namespace k3
 }  // namespace cv

@@ -135,6 +135,17 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
     const int halves = ew / 4;  // list owners per (CTA, query)
     int rc;
     if ((rc = raise_smem_limit(kernel))) return rc;
+    // Two-pass first tile (PILOT instantiations): pays where the first tile's insertion burst is a visible share of the
+    // scan -- single CTAs with up to 80 tiles each, i.e. corpora of up to ~1.5M rows per GPU (1M x 384: -3 % at
+    // B = 16...128, 100k rows: -25 %); at 158 tiles per CTA (3M rows) the pilot kernel's slightly slower tile loop
+    // already costs more than the burst it saves (+2.5 %), and CTA pairs measured neutral to negative.
+    // (CODDVEC_K3_PILOT=0|1 forces it: A/B switch.)
+    static const int pilot_env = getenv("CODDVEC_K3_PILOT") ? atoi(getenv("CODDVEC_K3_PILOT")) : -1;
+    MmaKernel pilot_kernel = nullptr;
+    if (cg == 1 && ew == 4 && !dump && fused_tail && pilot_env != 0) {
+        pilot_kernel = pick_mma_kernel_pilot(m.k);
+        if ((rc = raise_smem_limit(pilot_kernel))) return rc;
+    }
     // batches larger than one wave of query tiles are processed in slices (stream order keeps the scratch safe)
     int done = 0;
     while (done < m.B) {
@@ -251,7 +262,8 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
             attr[1].val.programmaticStreamSerializationAllowed = 1;
             cfg.numAttrs = 2;
         }
-        MMA_CUDA(cudaLaunchKernelEx(&cfg, kernel, tq, te, a));
+        const bool pilot = pilot_kernel != nullptr && P >= m.k && P > 1 && P <= 160 && (pilot_env == 1 || n_tiles <= 80 * P);
+        MMA_CUDA(cudaLaunchKernelEx(&cfg, pilot ? pilot_kernel : kernel, tq, te, a));
         if (launches) launches->fetch_add(1);
         if (!fused_tail) {
             // k > 64 / score dump: per-CTA lists [P][Bpad][k] -> K4, then clear the thresholds the scan left behind

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Write profiles/traffic.json -- the per-launch DRAM bytes bench.py reports as `roofline.traffic` -- from an
-`ncu --set full` summary (profiles/summarise_ncu.py output), stamped with the hash of the kernel sources in the
-working tree.  bench.py only reports an entry whose stamp equals the hash of the sources it runs, so this must be run
+`ncu --set full` summary (profiles/summarise_ncu.py output), stamped with the hash of that kernel's sources in the
+working tree (bench.KERNEL_SOURCES).  bench.py only reports an entry whose stamp equals the hash of the sources it runs, so this must be run
 on the tree the capture was taken from, with no kernel edits in between.
 
     python profiles/make_traffic.py SUMMARY.json  k_scan_topk=LABEL:rows:dim:batch  k_mma_topk=LABEL:rows:dim:batch
@@ -36,7 +36,7 @@ def main():
             "bytes_per_launch": to_bytes(launch["dram__bytes_read.sum"]) + to_bytes(launch["dram__bytes_write.sum"]),
             "rows": int(rows), "dim": int(dim), "batch": int(batch),
             "kernel_name": launch["Kernel Name"][0],
-            "kernel_source_hash": kernel_source_hash(),
+            "kernel_source_hash": kernel_source_hash(kernel),
             "source": f"profiles/{os.path.basename(summary_path)} [{label}] (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)",
         }
     with open(os.path.join(ROOT, "profiles", "traffic.json"), "w") as f:
