@@ -12,6 +12,7 @@
 #include <mutex>
 #include <shared_mutex>
 #include <string>
+#include <map>
 #include <unordered_map>
 #include <vector>
 
@@ -270,13 +271,16 @@ int plan_scan(cv_index* idx, QueryCtx* c, int qb, int k, bool pred, ScanLaunch* 
         return b;
     };
     const size_t smem = smem_for(k);
-    // The dynamic shared-memory limit is a per-function, process-wide attribute and one function serves every k (and
-    // every index of this dimension class): only ever raise it, to what the largest k needs.
+    // The dynamic shared-memory limit is an attribute per function AND device, shared by the whole process, and one
+    // function serves every k (and every index of this dimension class): only ever raise it, to what the largest k
+    // needs -- on every device the function is launched on (a striped collection runs it on several).
     {
         static std::mutex attr_mu;
-        static std::unordered_map<const void*, size_t> attr_set;
+        static std::map<std::pair<int, const void*>, size_t> attr_set;
         std::lock_guard<std::mutex> g(attr_mu);
-        size_t& have = attr_set[reinterpret_cast<const void*>(fn)];
+        int dev = 0;
+        CV_CUDA(cudaGetDevice(&dev));
+        size_t& have = attr_set[{dev, reinterpret_cast<const void*>(fn)}];
         const size_t want = smem_for(CV_MAX_K);
         if (have < want) {
             CV_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(want)));

@@ -60,17 +60,20 @@ std::string& mma_error() { return g_mma_err; }
         }                                                                                               \
     } while (0)
 
-// The dynamic shared-memory limit is a per-function, process-wide attribute: raise it to the architectural maximum
-// once per kernel instead of setting it to each launch's need (a later, smaller setting would make a concurrent or
-// cached larger launch fail).
+// The dynamic shared-memory limit is an attribute per function and device, shared by the whole process: raise it to
+// the architectural maximum once per (kernel, device) instead of setting it to each launch's need (a later, smaller
+// setting would make a concurrent or cached larger launch fail).  Per DEVICE: a striped collection launches the same
+// kernels on several GPUs from one process.
 int raise_smem_limit(MmaKernel kernel) {
     static std::mutex mu;
-    static std::vector<MmaKernel> done;
+    static std::vector<std::pair<int, MmaKernel>> done;
     std::lock_guard<std::mutex> g(mu);
-    for (MmaKernel k : done)
-        if (k == kernel) return 0;
+    int dev = 0;
+    MMA_CUDA(cudaGetDevice(&dev));
+    for (const auto& d : done)
+        if (d.first == dev && d.second == kernel) return 0;
     MMA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemLimit)));
-    done.push_back(kernel);
+    done.emplace_back(dev, kernel);
     return 0;
 }
 
