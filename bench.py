@@ -112,7 +112,8 @@ class ClockSampler:
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
                0x80: "hw_power_brake_slowdown"}
 
-    def __init__(self, device_index: int):
+    def __init__(self, device_index: int, period_s: float = 0.01):
+        self.period_s = period_s
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
         self._thr = None
@@ -137,7 +138,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.01)
+            self._stop.wait(self.period_s)
 
     def __enter__(self):
         if self._nv is not None:
@@ -559,13 +560,17 @@ def sweep_small_configs(torch, native, D, k, pk):
                 for _ in range(5):
                     fn()
                 torch.cuda.synchronize()
+            # SUSTAINED rate: >= 100 launches and >= 50 ms per timed loop, clocks sampled during it -- under the power
+            # cap a short burst (tests/quick_probe.py: 20 launches) runs 5-20 % faster than this, and the tensor-heavy
+            # batches the most
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            iters = 100 if B <= 256 else 30
-            e0.record()
-            for _ in range(iters):
-                fn()
-            e1.record()
-            torch.cuda.synchronize()
+            iters = 400 if B <= 256 else 100
+            with ClockSampler(torch.cuda.current_device(), period_s=0.002) as clk:
+                e0.record()
+                for _ in range(iters):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / iters
             st = idx.stats()
             bytes_alg = rows * (2 * st.dim_padded + 4)
@@ -575,7 +580,8 @@ def sweep_small_configs(torch, native, D, k, pk):
                         "path": "mma" if st.last_path == native.PATH_MMA else "scan",
                         "scan_gbs_single_pass": bytes_alg / ms / 1e6, "tflops": flops / ms / 1e9,
                         "hbm_frac_single_pass": bytes_alg / ms / 1e6 / pk["hbm_gbs"],
-                        "ideal_ms": ideal_ms, "frac_of_roofline": ideal_ms / ms,
+                        "ideal_ms": ideal_ms, "frac_of_roofline": ideal_ms / ms, "launches_timed": iters,
+                        "sm_mhz": clk.summary()["sm_mhz"], "throttle_reasons": clk.summary()["reasons"],
                         "roofline_note": "ideal = max(one pass of the algorithmic bytes at the measured HBM peak, flops at the "
                                          "sustained bf16 peak); the whole batch incl. every launch it needs"})
         idx.close()
