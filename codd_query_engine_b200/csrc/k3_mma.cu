@@ -81,6 +81,7 @@ int raise_smem_limit(MmaKernel kernel) {
 // All of it is zero between launches (the fused tail's last owner of a query clears what the query dirtied), so it
 // is zeroed once, when (re)allocated.
 constexpr size_t kDebugBytes = 64 + (296 * 16 + 64 * 6) * sizeof(unsigned long long);  // CODDVEC_K3_DEBUG words + CODDVEC_K3_TIMELINE stamps
+constexpr size_t kProgBytes = 296 * sizeof(unsigned long long);                          // super-tile progress words (one per unit)
 
 size_t mma_state_bytes(int queries) {
     return ((static_cast<size_t>(queries) * (kHeadsLd + 3) + 4) * sizeof(uint32_t) + 63) / 64 * 64;
@@ -176,8 +177,8 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
             scratch.state = nullptr;
             scratch.state_q = 0;
             const int cap_q = std::max(Bpad, 1024);
-            MMA_CUDA(cudaMalloc(&scratch.state, mma_state_bytes(cap_q) + kDebugBytes));  // (+ debug words, timeline)
-            MMA_CUDA(cudaMemsetAsync(scratch.state, 0, mma_state_bytes(cap_q) + kDebugBytes, m.stream));
+            MMA_CUDA(cudaMalloc(&scratch.state, mma_state_bytes(cap_q) + kDebugBytes + kProgBytes));  // (+ debug words, timeline, progress)
+            MMA_CUDA(cudaMemsetAsync(scratch.state, 0, mma_state_bytes(cap_q) + kDebugBytes + kProgBytes, m.stream));
             scratch.state_q = cap_q;
         }
         __nv_bfloat16* qb = reinterpret_cast<__nv_bfloat16*>(scratch.p);
@@ -231,6 +232,16 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
         a.cosine = m.cosine ? 1 : 0;
         a.split = split ? 1 : 0;
         a.fused_tail = fused_tail ? 1 : 0;
+        // lockstep of sibling super-tiles (CODDVEC_K3_LOCKSTEP=<window in tiles>, 0 = off: A/B switch)
+        static const int lock_window = getenv("CODDVEC_K3_LOCKSTEP") ? atoi(getenv("CODDVEC_K3_LOCKSTEP")) : 4;
+        // (two super-tiles stay together on their own -- 1.1x at 12.5M rows -- and short scans end before anybody has
+        // drifted: 1.00x at 1M rows, 1.14x at 4M; the lockstep is for three or more super-tiles on long scans)
+        static const int lock_min_tiles = getenv("CODDVEC_K3_LOCKSTEP_MIN_TILES") ? atoi(getenv("CODDVEC_K3_LOCKSTEP_MIN_TILES")) : 1000;
+        a.prog = (QT > 2 && lock_window > 0 && n_tiles >= static_cast<int64_t>(lock_min_tiles) * P)
+                     ? reinterpret_cast<unsigned long long*>(scratch.state + mma_state_bytes(scratch.state_q) + kDebugBytes)
+                     : nullptr;
+        a.epoch = ++scratch.epoch;
+        a.lock_window = lock_window;
         a.cand = lists;
         a.cand_ld = P * halves * m.k;
         a.cnt = cnt;

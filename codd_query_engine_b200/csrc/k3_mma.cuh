@@ -12,6 +12,7 @@ struct MmaScratch {  // device scratch owned by the query context, grown on dema
     size_t cap = 0;
     unsigned char* state = nullptr;  // cross-CTA thresholds / counters for state_q queries: zero between launches (self-resetting)
     int state_q = 0;
+    uint32_t epoch = 0;              // launch counter: tags the super-tile progress words (stale tags are ignored, no reset needed)
 };
 
 struct MmaArgs {
