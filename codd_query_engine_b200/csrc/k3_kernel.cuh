@@ -5,19 +5,27 @@
 // exact scan:  S[q][row] = (Qhat_bf16[q] . E_bf16[row]) * scale[row], fp32 accumulate in TMEM.
 //
 // Shape of the work.  The query tile is the UMMA *M* operand (128 queries = 128 TMEM lanes, resident
-// in shared memory for the whole kernel), a tile of 128 corpus rows is the *N* operand (streamed once
-// from HBM by TMA, K-major, SWIZZLE_128B, 64-element K blocks through a 6-deep mbarrier ring), D is
+// in shared memory for the whole kernel up to 512-d), a tile of 128 corpus rows is the *N* operand (streamed once
+// from HBM by TMA, K-major, SWIZZLE_128B, 64-element K blocks through an up-to-8-deep mbarrier ring), D is
 // the short K dimension (Dp/16 tcgen05.mma per tile).  With queries on the lanes every epilogue
 // thread owns ONE query: it keeps that query's running threshold in a register and its k-list
-// privately, so the fused top-k needs no atomics, no shuffles and no shared memory -- one FMUL +
-// one FSETP per score, and the B x N score matrix never leaves TMEM/registers.  The per-row scale
+// privately, so the fused top-k needs no atomics, no shuffles and no shared memory -- a max-reduction of the raw
+// dots per 32-column chunk against a slightly relaxed threshold, exact scaling only on the chunks that pass --
+// and the B x N score matrix never leaves TMEM/registers.  The per-row scale
 // and the namespace / label / bitmask predicate are folded into one shared-memory vector per tile
 // (NaN = not eligible, so an ineligible score fails every comparison).
 //
-// Warp roles (192 threads, one CTA per SM, persistent): warp 0 = TMA producer (one elected lane),
-// warp 1 = TMEM allocator + MMA issuer (one elected lane), warps 2..5 = epilogue (TMEM lane quarter
-// = warp_id % 4).  Two TMEM accumulator stages (2 x 128 columns) overlap the MMAs of tile t+1 with the
-// epilogue of tile t.
+// Warp roles (224 threads with four epilogue warps, one CTA per SM, persistent): warp 0 = TMA producer (one elected
+// lane), warp 1 = TMEM allocator + MMA issuer (one elected lane), warps 2..5 = epilogue (TMEM lane quarter
+// = warp_id % 4), last warp = bound warp (keeps the cross-CTA lower bound of each duty query's k-th best fresh, off
+// the epilogue's critical path).  All 512 TMEM columns are accumulator stages -- four of 128 columns for single
+// CTAs, two of 256 for CTA pairs -- so the MMAs of the next tiles overlap the epilogue of tile t and a burst of list
+// insertions does not stop the HBM stream.
+//
+// What keeps the fixed costs down on short scans (profiles/README.md, round 2): query prep as a programmatic
+// dependent launch, rank-based list insertion, heads published once per tile, the bound warp, a two-pass first tile
+// (PILOT instantiations), a per-query last-owner merge instead of a merge launch, self-resetting cross-CTA state;
+// on long scans with several query super-tiles: their lockstep (HBM reads every tile once for all of them).
 //
 // Roofline: algorithmic bytes = rows * (2*Dp + 4) per query tile pass, flops =
 // 2 * B * rows * Dp.  HBM-bound for B <~ 200, tensor-bound above.
@@ -1091,8 +1099,8 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
         // every row the grid has scanned.  Each query has ONE duty CTA (p == query % P): its bound warp re-reads the
         // query's heads row over and over (coalesced, one L2 round trip), ranks it with warp reductions and raises
         // gthr[q], which every epilogue thread reads once per tile anyway.  (When the epilogue threads ranked the heads
-        // themselves -- all 148 CTAs x 128 threads at the same tiles -- the loads queued in L2 and each refresh held
-        // the scan for 10-30 us: per-tile trace, profiles/README.md.)
+        // themselves -- every live thread its own query's 148 heads, at tiles 1, 4, 16, ... and before the last tile --
+        // each refresh held its CTA's epilogue for 7-12 us: per-tile trace, profiles/README.md.)
         volatile uint32_t* const scan_done = tmem_slot + 1;
         volatile uint32_t* const bound_ack = tmem_slot + 2;
         constexpr int J = 5;                               // 32 * J >= P (at most 148 list owners per column half)
