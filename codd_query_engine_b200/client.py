@@ -118,6 +118,11 @@ class Collection:
         self._columns = MetadataColumns()   # dictionary-encoded metadata fields `where` clauses have touched
         self._generation = 0                # bumped by every write: keys the compiled-where cache
         self._where_cache: dict[str, tuple[int, Any]] = {}
+        # the snapshot this collection was loaded from / last saved to (cross-process hand-over: see _maybe_reload)
+        self._snap_dir: Optional[str] = None
+        self._snap_mtime_ns = 0
+        self._snap_generation = -1          # _generation when the snapshot and this object last agreed
+        self._snap_checked = 0.0
 
     # ------------------------------------------------------------------ helpers
     def _ensure_index(self, dim: int) -> NativeIndex:
@@ -362,6 +367,7 @@ class Collection:
 
     # ------------------------------------------------------------------ reads
     def count(self) -> int:
+        self._maybe_reload()
         with self._lock:
             return len(self._row_of)
 
@@ -386,6 +392,8 @@ class Collection:
     def get(self, ids=None, where=None, limit: Optional[int] = None, offset: Optional[int] = None, include=None,
             **_ignored) -> dict:
         include = self._check_include(include, _GET_INCLUDE)
+        if self._snap_dir is not None:
+            self._maybe_reload()
         with self._lock:
             if ids is not None:
                 rows = [self._row_of[i] for i in _as_list(ids) if i in self._row_of]
@@ -433,6 +441,8 @@ class Collection:
             return self._batcher
 
     def _query_direct(self, query_embeddings=None, query_texts=None, n_results: int = 10, where=None, include=None) -> dict:
+        if self._snap_dir is not None:
+            self._maybe_reload()
         include = self._check_include(include, _QUERY_INCLUDE)
         if (query_embeddings is None) == (query_texts is None):
             raise ValueError("You must provide exactly one of query_embeddings or query_texts")
@@ -604,6 +614,63 @@ class Collection:
             coll._ensure_index(dim).load_rows(vec, scale, ns, lb)
         return coll
 
+    # ------------------------------------------------------------------ cross-process hand-over
+    # The reference's indexer job and its service talk to ONE Chroma server; here each process has its own GPU-resident
+    # collections and the snapshot directory (CODDVEC_SNAPSHOT_DIR) plays the server's volume: the job's collections
+    # are written there when it exits, and a collection that was loaded from a snapshot looks -- at most once per
+    # CODDVEC_SNAPSHOT_RELOAD_S (default 1 s; 0 = never) -- whether a newer snapshot has appeared and adopts it in
+    # place, so a long-lived service (one client, one store object: codd_lib/.../promql_module.py:59-67) sees what the
+    # job indexed without a restart.  A collection with local writes since its snapshot keeps them.
+    _STATE = ("metadata", "_metric", "_label_field", "_index", "_row_of", "_ids", "_metadatas", "_documents", "_alive",
+              "_free_rows", "_ns_codes", "_label_codes", "_ns_rows", "_columns")
+
+    def _bind_snapshot(self, directory: str) -> None:
+        with self._lock:
+            self._snap_dir = os.path.abspath(directory)
+            self._snap_mtime_ns = os.stat(os.path.join(self._snap_dir, "meta.json")).st_mtime_ns
+            self._snap_generation = self._generation
+
+    def _maybe_reload(self, force: bool = False) -> bool:
+        d = self._snap_dir
+        if d is None:
+            return False
+        interval = float(os.environ.get("CODDVEC_SNAPSHOT_RELOAD_S", "1.0"))
+        now = time.monotonic()
+        if interval <= 0 or (not force and now - self._snap_checked < interval):
+            return False
+        self._snap_checked = now
+        try:
+            mtime = os.stat(os.path.join(d, "meta.json")).st_mtime_ns
+        except OSError:
+            return False
+        if mtime <= self._snap_mtime_ns:
+            return False
+        with self._lock:
+            if self._generation != self._snap_generation:  # local writes since the snapshot: they win
+                self._snap_mtime_ns = mtime
+                return False
+        try:
+            fresh = Collection.load(d, self._embed, device=self._device)  # (uploads to the GPU outside the lock)
+        except (OSError, ValueError):  # the writer is replacing the directory right now: look again next time
+            return False
+        with self._lock:
+            if self._generation != self._snap_generation:
+                fresh.close()
+                return False
+            while self._inflight:
+                self._idle.wait()
+            old = self._index
+            for attr in self._STATE:
+                setattr(self, attr, getattr(fresh, attr))
+            fresh._index = None
+            self._generation += 1
+            self._where_cache.clear()
+            self._snap_mtime_ns = mtime
+            self._snap_generation = self._generation
+        if old is not None:
+            old.close()
+        return True
+
     # ------------------------------------------------------------------ extras
     def stats(self):
         """Device-side counters (rows, launches, last query ms/bytes, path) -- SURVEY.md section 5."""
@@ -679,7 +746,10 @@ class Client:
                 with open(os.path.join(d, "meta.json"), encoding="utf-8") as f:
                     name = json.load(f)["name"]
                 if name not in self._reg.collections:
-                    self._reg.collections[name] = Collection.load(d, self._embedding_function, device=self._device)
+                    coll = self._reg.collections[name] = Collection.load(d, self._embedding_function, device=self._device)
+                    coll._bind_snapshot(d)
+                else:  # another process may have written a newer snapshot since this one loaded it
+                    self._reg.collections[name]._maybe_reload()
 
     def persist(self, path: Optional[str] = None) -> str:
         """Write every collection of this client to `path` (default: the PersistentClient path)."""
@@ -692,6 +762,7 @@ class Client:
         for coll in colls:
             keep.add(self._dir_name(coll.name))
             coll.save(os.path.join(root, self._dir_name(coll.name)))
+            coll._bind_snapshot(os.path.join(root, self._dir_name(coll.name)))
         # collections deleted since the last persist() must not come back on the next load
         if os.path.isdir(root):
             import shutil
@@ -773,8 +844,9 @@ def HttpClient(host: str = "localhost", port: int = 8000, **kwargs) -> Client:  
     codd_jobs/metrics_semantic_indexer_main.py:209-212): the "server" is this process's GPU.
 
     The stand-in is PER PROCESS: an indexer job and a service that ran against one Chroma server share data here
-    only through snapshots -- the job calls ``client.persist()`` (or sets CODDVEC_SNAPSHOT_DIR and persists at exit),
-    the service loads them when it builds its first client."""
+    through snapshots.  With CODDVEC_SNAPSHOT_DIR set, a process that wrote to its collections persists them when it
+    exits (or whenever it calls ``client.persist()``), and a process that loaded a collection from a snapshot adopts
+    a newer snapshot in place within CODDVEC_SNAPSHOT_RELOAD_S (Collection._maybe_reload)."""
     kwargs.pop("ssl", None)
     kwargs.pop("headers", None)
     kwargs.pop("settings", None)
@@ -785,7 +857,41 @@ def HttpClient(host: str = "localhost", port: int = 8000, **kwargs) -> Client:  
     if snap:
         client._path = os.path.join(os.path.abspath(snap), f"{host}_{int(port)}")
         client._load_snapshots()
+        _persist_at_exit(client)
     return client
+
+
+_EXIT_HOOKS: set = set()
+
+
+def _persist_modified(client: Client) -> list:
+    """Write the collections of `client`'s endpoint that changed since their snapshot (or never had one) to the
+    client's snapshot directory; returns their names.  What an unmodified indexer job gets at exit."""
+    with client._reg.lock:
+        colls = [c for c in client._reg.collections.values() if c._generation != c._snap_generation and c._index is not None]
+    for coll in colls:  # (a collection that came from a snapshot goes back to it; new ones under the client's directory)
+        if coll._snap_dir is None and client._path is None:
+            raise ValueError(f"collection {coll.name!r} has no snapshot directory to go to")
+        d = coll._snap_dir or os.path.join(client._path, client._dir_name(coll.name))
+        coll.save(d)
+        coll._bind_snapshot(d)
+    return [c.name for c in colls]
+
+
+def _persist_at_exit(client: Client) -> None:
+    """Once per endpoint: at interpreter exit, persist what this process wrote (CODDVEC_SNAPSHOT_AT_EXIT=0 disables)."""
+    if os.environ.get("CODDVEC_SNAPSHOT_AT_EXIT", "1") in ("0", "") or client.endpoint in _EXIT_HOOKS:
+        return
+    _EXIT_HOOKS.add(client.endpoint)
+    import atexit
+
+    def hook(c=client):
+        try:
+            _persist_modified(c)
+        except Exception as exc:  # noqa: BLE001 - exit path: report, never raise
+            print(f"coddvec: snapshot at exit failed: {exc}", file=__import__("sys").stderr)
+
+    atexit.register(hook)
 
 
 def PersistentClient(path: str = "./chroma", **kwargs) -> Client:  # noqa: N802

@@ -357,3 +357,57 @@ def test_failed_upsert_keeps_tombstones_and_metadata_updates_reach_the_device(cl
     assert coll.get(where={"namespace": "n2"})["ids"] == ["a"]
     coll.update(ids=["d"], embeddings=x[3:4] * 2, metadatas=[{"extra": 1}])                  # with embeddings: merged too
     assert coll.get(ids=["d"])["metadatas"] == [{"namespace": "n1", "category": "k", "extra": 1}]
+
+
+def test_snapshot_hand_over_between_processes(client, tmp_path, monkeypatch):
+    """The indexer job and the service are two processes with one snapshot directory between them (the stand-in for
+    the Chroma server's volume): what the 'job' persists, a 'service' collection that was loaded from the older
+    snapshot adopts IN PLACE (its store keeps the same Collection object) -- unless it has local writes of its own."""
+    monkeypatch.setenv("CODDVEC_SNAPSHOT_RELOAD_S", "0.000001")
+    x = vecs(60, d=64, seed=3)
+    job = client.get_or_create_collection("metrics", metadata=COSINE)
+    job.upsert(ids=[f"m{i}" for i in range(40)], embeddings=x[:40], metadatas=[{"namespace": "a"}] * 40)
+    root = client.persist(str(tmp_path / "vol"))
+    d = str(next((tmp_path / "vol").iterdir()))
+    service = client_mod.Collection.load(d, device=client._device)  # "another process": its own object, its own index
+    service._bind_snapshot(d)
+    try:
+        assert service.count() == 40
+        assert service.query(query_embeddings=x[50:51], n_results=1)["ids"][0][0] != "m50"
+        # the job indexes more and persists again; the service sees it at its next read, same object
+        job.upsert(ids=[f"m{i}" for i in range(40, 60)], embeddings=x[40:], metadatas=[{"namespace": "b"}] * 20)
+        assert client_mod._persist_modified(client) == ["metrics"] and client_mod._persist_modified(client) == []
+        assert service.query(query_embeddings=x[50:51], n_results=1)["ids"] == [["m50"]]
+        assert service.count() == 60 and service.get(ids=["m59"])["metadatas"] == [{"namespace": "b"}]
+        assert service.query(query_embeddings=x[50:51], n_results=1, where={"namespace": "a"})["ids"][0][0] != "m50"
+        # local writes win: a service that has written itself does not adopt the job's next snapshot
+        service.upsert(ids=["local"], embeddings=x[:1] * 2)
+        job.delete(ids=["m0"])
+        client.persist(root)
+        assert service.count() == 61 and service.get(ids=["m0"])["ids"] == ["m0"]
+    finally:
+        service.close()
+
+
+def test_http_client_persists_at_exit_and_reloads(monkeypatch, tmp_path):
+    """CODDVEC_SNAPSHOT_DIR wiring for unmodified callers: HttpClient registers the exit hook once per endpoint; the
+    hook writes what changed; the next process's first client loads it."""
+    monkeypatch.setattr(client_mod, "NativeIndex", OracleIndex)
+    monkeypatch.setenv("CODDVEC_SNAPSHOT_DIR", str(tmp_path))
+    registered = []
+    monkeypatch.setattr("atexit.register", lambda fn, *a, **k: registered.append(fn))
+    c1 = client_mod.HttpClient(host="chroma", port=8123)
+    c1b = client_mod.HttpClient(host="chroma", port=8123)
+    assert len(registered) == 1  # once per endpoint
+    c1.get_or_create_collection("m").upsert(ids=["a", "b"], embeddings=vecs(2, d=32))
+    registered[0]()  # "the job exits"
+    assert (tmp_path / "chroma_8123" / "m" / "meta.json").is_file()
+    c1.reset()
+    c1b.reset()
+    client_mod._EXIT_HOOKS.discard(c1.endpoint)
+    c2 = client_mod.HttpClient(host="chroma", port=8123)  # "the service starts"
+    try:
+        assert c2.get_collection("m").count() == 2
+    finally:
+        c2.reset()
+        client_mod._EXIT_HOOKS.discard(c2.endpoint)
