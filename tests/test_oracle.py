@@ -223,3 +223,33 @@ def test_oracle_matches_chroma_golden():
             gap = np.diff(np.sort(np.asarray(doc["exact_fp32_distances"][b])))
             if gap.min() > 2e-3:
                 assert list(r[b]) == list(exact[b]), f"{name}: query {b} rows differ"
+
+
+@pytest.mark.parametrize("D", [64, 384, 768])
+def test_oracle_agrees_with_independent_cosine_implementations(D):
+    """Not the reference's dependency (chromadb / hnswlib are not installable here, so the oracle stays "unpinned" in
+    the sense of DESIGN.md section 2) -- but two independent third-party implementations of the SAME definition
+    hnswlib's cosine space uses, distance = 1 - x.q / (|x| |q|): scikit-learn's brute-force NearestNeighbors and
+    scipy's cdist, fed the vectors the oracle actually stores (bf16 rows widened to fp32).  Distances agree to fp32
+    rounding and the neighbour lists are identical wherever the k-th and (k+1)-th distances are further apart than that."""
+    sk = pytest.importorskip("sklearn.neighbors")
+    sp = pytest.importorskip("scipy.spatial.distance")
+    rng = np.random.default_rng(D)
+    n, B, k = 5000, 20, 10
+    x = rng.standard_normal((n, D)).astype(np.float32)
+    x[n // 2] = x[7]  # one exact duplicate: a tie, broken by row id in the oracle
+    q = np.concatenate([x[7:8], rng.standard_normal((B - 1, D)).astype(np.float32)])
+    stored, scale = bf.normalise_store(x)
+    scores, rows, counts = bf.query(stored, scale, q, k)
+    wide = bf.bf16_bits_to_f32(stored).astype(np.float64)  # what the index holds
+    dist_sk, idx_sk = sk.NearestNeighbors(n_neighbors=k + 1, metric="cosine", algorithm="brute").fit(wide).kneighbors(q.astype(np.float64))
+    full = sp.cdist(q.astype(np.float64), wide, metric="cosine")  # [B][n]
+    assert (counts == k).all()
+    for b in range(B):
+        ours = 1.0 - scores[b].astype(np.float64)
+        assert np.abs(ours - full[b, rows[b]]).max() < 5e-6            # every reported distance is scipy's for that row
+        assert np.abs(ours - dist_sk[b, :k]).max() < 5e-6              # and the k smallest are scikit-learn's k smallest
+        gap = dist_sk[b, k] - dist_sk[b, k - 1]
+        if gap > 1e-5 and np.diff(dist_sk[b, :k]).min() > 1e-5:         # well separated: identical lists, same order
+            assert rows[b].tolist() == idx_sk[b, :k].tolist()
+    assert rows[0, 0] == 7 and rows[0, 1] == n // 2                     # the duplicate pair: lower row id first
