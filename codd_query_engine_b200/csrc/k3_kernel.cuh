@@ -57,8 +57,8 @@ constexpr int kMaxStages = 8;    // corpus ring depth: as many 16 KiB stages as 
 constexpr int kMaxAccStages = 4;
 // TMEM accumulator stages: all 512 columns either way -- four 128-column stages for single CTAs, two 256-column
 // stages for CTA pairs.  The stages are the slack between the MMA stream and the epilogue: a burst of list insertions
-// (every CTA's first tile) or a heads-bound refresh holds the epilogue for 5-8 us, and the HBM stream only keeps
-// running through it while the MMA issuer still has a free accumulator to write.
+// (every CTA's first tiles) holds the epilogue for several microseconds, and the HBM stream only keeps running through
+// it while the MMA issuer still has a free accumulator to write.
 __host__ __device__ constexpr int acc_stages(int cg) { return cg == 1 ? 4 : 2; }
 // threads per CTA: producer warp + MMA warp + EW epilogue warps (4, or 8: two warps per TMEM lane quarter on alternate
 // column chunks) + the bound warp
@@ -1013,15 +1013,15 @@ k_mma_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ C
             while (*reinterpret_cast<volatile uint32_t*>(tmem_slot + 2) == 0u) {}
         if (tl && et == 0) {
             tl[5] = global_timer_ns();                          // 5: last tile scanned
-            tl[10] = e_top;                                     // 10: epilogue loop top (scales, bounds, refreshes, bar.sync)
+            tl[10] = e_top;                                     // 10: epilogue loop top (scales, shared bound, bar.sync)
             tl[11] = e_wait;                                    // 11: epilogue waited for an accumulator (it was ahead)
             tl[12] = e_scan;                                    // 12: TMEM loads + score scan + insertions
         }
         if (fused_tail) {
             // ---- fused tail: no merge launch.  A single list owner: its list is final.  Otherwise every owner
             // publishes the keys that can still be in the global top-k -- score >= the largest shared lower bound it
-            // knows (every CTA's k-th best through gthr, the heads bound refreshed before the last tile): both bound
-            // the global k-th best from below, so every global top-k key survives in its owner.
+            // knows (gthr: every owner's k-th best and the bound warps' k-th largest head): both bound the global k-th
+            // best from below, so every global top-k key survives in its owner.
             if (owners == 1) {
                 if (live) {
 #pragma unroll

@@ -122,9 +122,11 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
         return mma_fail(CV_ERR_UNSUPPORTED, "tensor-core path: query tile does not fit shared memory at dim " + std::to_string(m.Dp));
     // (CODDVEC_K3_SPLIT_LAUNCHES: bit 0 = separate query-prep launch, bit 1 = separate merge launch -- A/B switches)
     static const int split_launches = getenv("CODDVEC_K3_SPLIT_LAUNCHES") ? atoi(getenv("CODDVEC_K3_SPLIT_LAUNCHES")) : 0;
-    // The query tile is built inside the kernel when that is cheap -- up to 16 queries (every CTA normalises them
-    // again, ~0.4 us per query) or short rows (the hi/lo split's second tile only exists in shared memory) --
-    // otherwise once, by k_prep_queries, and fetched by TMA: 128 live rows per CTA cost 25 us against 5 us.
+    // The query tile is built once, by k_prep_queries, and fetched by TMA; k_mma_topk is launched as its programmatic
+    // dependent, so the prep hides behind the main kernel's prologue and first corpus loads (same-box A/B: that beat
+    // building the tile inside every CTA even for four queries, 0.143 against 0.146 ms at 1M rows).  Only the hi/lo
+    // split builds its tiles inside the kernel (its second tile exists in shared memory only).
+    // (CODDVEC_K3_FUSED_PREP_MAX_B=<B> builds the tile in-kernel for batches up to B: A/B switch.)
     static const int fused_prep_max_b = getenv("CODDVEC_K3_FUSED_PREP_MAX_B") ? atoi(getenv("CODDVEC_K3_FUSED_PREP_MAX_B")) : 0;
     const bool fused_prep = q_resident && kblocks <= 8 && (split || (m.B <= fused_prep_max_b && !(split_launches & 1)));
     const bool fused_tail = m.k <= 64 && m.dump == nullptr && !(split_launches & 2);          // register-resident lists
@@ -186,7 +188,7 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
         uint32_t* heads = reinterpret_cast<uint32_t*>(scratch.state);                    // [state_q][kHeadsLd], 16-byte aligned rows
         uint32_t* gthr = heads + static_cast<size_t>(scratch.state_q) * kHeadsLd;         // [state_q]
         uint32_t* cnt = gthr + scratch.state_q;                                           // [state_q]
-        uint32_t* group_done = cnt + scratch.state_q;                                     // [state_q]
+        uint32_t* owners_done = cnt + scratch.state_q;                                    // [state_q]
 
         CUtensorMap tq, te;
         memset(&tq, 0, sizeof(tq));
@@ -245,7 +247,7 @@ int mma_enqueue(const MmaArgs& m, MmaScratch& scratch, std::atomic<int64_t>* lau
         a.cand = lists;
         a.cand_ld = P * halves * m.k;
         a.cnt = cnt;
-        a.done = group_done;
+        a.done = owners_done;
         a.out = m.out + static_cast<size_t>(done) * m.k;
         static const bool debug = getenv("CODDVEC_K3_DEBUG") != nullptr;
         a.dbg = debug ? reinterpret_cast<unsigned long long*>(scratch.state + mma_state_bytes(scratch.state_q)) : nullptr;
