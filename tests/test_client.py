@@ -411,3 +411,22 @@ def test_http_client_persists_at_exit_and_reloads(monkeypatch, tmp_path):
     finally:
         c2.reset()
         client_mod._EXIT_HOOKS.discard(c2.endpoint)
+
+
+def test_metadata_columns_agree_with_row_by_row_evaluation_on_mixed_types():
+    """The dictionary-encoded column store must answer exactly like `evaluate` row by row, also where Python's
+    equality is loose (1 == 1.0 == True) and where rows lack the field, are empty or deleted."""
+    from codd_query_engine_b200.where import MetadataColumns
+
+    mds = [{"a": 1}, {"a": 1.0}, {"a": True}, {"a": "1"}, None, {}, {"b": 2}, {"a": 0}, {"a": False}, {"a": 2.5}] * 7
+    cols = MetadataColumns()
+    clauses = [{"a": 1}, {"a": {"$in": [1, "1"]}}, {"a": {"$nin": [0]}}, {"a": {"$ne": 1}}, {"a": True}, {"a": {"$gt": 0}},
+               {"a": {"$lte": 1}}, {"b": {"$gte": 2}}, {"$or": [{"a": "1"}, {"b": 2}]}, {"$and": [{"a": {"$gt": 0}}, {"a": {"$lt": 2}}]}]
+    for where in clauses:
+        want = np.array([evaluate(where, md) for md in mds])
+        assert np.array_equal(cols.evaluate_rows(where, mds), want), where
+    cols.set_row(3, {"a": 1})   # writes after the first touch keep the column in step
+    cols.set_row(0, None)
+    mds[3], mds[0] = {"a": 1}, None
+    for where in clauses:
+        assert np.array_equal(cols.evaluate_rows(where, mds), np.array([evaluate(where, md) for md in mds])), where
