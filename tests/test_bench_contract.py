@@ -45,3 +45,24 @@ def test_our_arm_has_no_cpu_fallback():
         return  # on the GPU box the arm runs; the refusal is what is checked here
     out = run_bench("--rows", "1000", "--steps", "1", "--warmup", "1")
     assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
+
+
+def test_committed_traffic_stamps_match_the_kernel_sources():
+    """profiles/traffic.json is only reported while its stamps equal the hashes of the kernel sources in the tree
+    (bench.traffic_for).  A kernel edit without a fresh `ncu --set full` capture must be noticed here, not by a
+    `"traffic": null` in the driver's bench line: re-capture (tests/gpu_round2_final5.sh) and re-stamp
+    (profiles/make_traffic.py)."""
+    import json
+    import os
+
+    import bench
+
+    doc = json.load(open(os.path.join(bench.ROOT, "profiles", "traffic.json")))
+    for kernel in ("k_scan_topk", "k_mma_topk"):
+        assert doc[kernel]["kernel_source_hash"] == bench.kernel_source_hash(kernel), \
+            f"{kernel}: sources changed since the ncu capture in {doc[kernel]['source']}"
+    got, note = bench.traffic_for("k_scan_topk", 100_000_000, 384, 1)
+    assert got is not None and abs(got / (100_000_000 * 772) - 1) < 0.01, note          # traffic == algorithmic bytes
+    got, note = bench.traffic_for("k_mma_topk", 100_000_000, 384, 1024)
+    assert got is not None and abs(got / (100_000_000 * 772) - 1) < 0.01, note
+    assert bench.traffic_for("k_mma_topk", 100_000_000, 384, 64)[0] is None             # no capture at that batch: never a guess
